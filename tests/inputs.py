@@ -1,0 +1,105 @@
+"""Seeded synthetic inputs shared by tests/, tests/golden/make_golden.py, bench.py and smoke().
+
+Everything is integer arithmetic on numpy Generators so the same seeds give the same bytes in
+the build container and on the GPU box.  Shapes follow SURVEY.md 8(d).
+"""
+import numpy as np
+
+NUM_WEIGHT_BYTES = 23184
+
+
+def tb_image(H=128, W=128):
+    """sim/top/tb.v:522-527 stimulus: pixel[i] = (i*13 + 5) % 256."""
+    i = np.arange(H * W, dtype=np.int64)
+    return ((i * 13 + 5) % 256).astype(np.uint8).reshape(H, W)
+
+
+def smooth_images(seed, n, H=128, W=128):
+    """Low-frequency images: integer bilinear upsample of a coarse random grid + small noise."""
+    rng = np.random.default_rng(seed)
+    step = 16
+    gh, gw = H // step + 1, W // step + 1
+    grid = rng.integers(0, 256, (n, gh, gw)).astype(np.int64)
+    ys, xs = np.arange(H), np.arange(W)
+    y0, fy = ys // step, ys % step
+    x0, fx = xs // step, xs % step
+    a = grid[:, y0][:, :, x0]
+    b = grid[:, y0][:, :, x0 + 1]
+    c = grid[:, y0 + 1][:, :, x0]
+    d = grid[:, y0 + 1][:, :, x0 + 1]
+    fy = fy[None, :, None]
+    fx = fx[None, None, :]
+    top = a * (step - fx) + b * fx
+    bot = c * (step - fx) + d * fx
+    img = (top * (step - fy) + bot * fy) // (step * step)
+    img = img + rng.integers(-6, 7, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def make_images(kind, n, H=128, W=128):
+    """kind: 'tb' | ('rng', seed) | ('smooth', seed) | ('const', value)."""
+    if kind == "tb":
+        return np.broadcast_to(tb_image(H, W), (n, H, W)).copy()
+    tag, arg = kind
+    if tag == "rng":
+        return np.random.default_rng(arg).integers(0, 256, (n, H, W), dtype=np.uint8)
+    if tag == "smooth":
+        return smooth_images(arg, n, H, W)
+    if tag == "const":
+        return np.full((n, H, W), arg, dtype=np.uint8)
+    raise ValueError(kind)
+
+
+def make_weights(kind, shipped=None):
+    """kind: 'shipped' | 'identity' | ('rng', seed) | ('const', byte) | ('sparse', seed)."""
+    if kind == "shipped":
+        assert shipped is not None and shipped.size == NUM_WEIGHT_BYTES
+        return np.array(shipped, dtype=np.uint8)
+    if kind == "identity":                      # tb.v:501-513: all zero except byte 4 (core 0, centre tap) = 1
+        w = np.zeros(NUM_WEIGHT_BYTES, dtype=np.uint8)
+        w[4] = 1
+        return w
+    tag, arg = kind
+    if tag == "rng":                            # full range: bytes 0..255 == s8 -128..127
+        return np.random.default_rng(arg).integers(0, 256, NUM_WEIGHT_BYTES, dtype=np.uint8)
+    if tag == "const":
+        return np.full(NUM_WEIGHT_BYTES, arg, dtype=np.uint8)
+    if tag == "sparse":                         # mostly zero taps (exercises the kv==0 skip, arm_cnn.c:101)
+        rng = np.random.default_rng(arg)
+        w = rng.integers(0, 256, NUM_WEIGHT_BYTES, dtype=np.uint8)
+        w[rng.random(NUM_WEIGHT_BYTES) < 0.8] = 0
+        return w
+    raise ValueError(kind)
+
+
+def make_fc(seed=1234, n_cls=6):
+    """Seeded (n_cls,1024) f32 classifier (the shipped fc_weight.npy is the stale (6,64) GAP one)."""
+    rng = np.random.default_rng(seed)
+    w = (rng.standard_normal((n_cls, 1024)) * 0.1).astype(np.float32)
+    b = (rng.standard_normal(n_cls) * 0.1).astype(np.float32)
+    return w, b
+
+
+# 128x128 cases pinned by tests/golden/conv_cases.npz (outputs produced by the reference itself).
+CONV_CASES = [
+    dict(name="tb_identity", weights="identity", images="tb", n=1, shifts=(0, 0, 0), dump=True),
+    dict(name="tb_shipped_default", weights="shipped", images="tb", n=1, shifts=(2, 4, 6), tail=True),
+    dict(name="rng_shipped_default", weights="shipped", images=("rng", 0), n=8, shifts=(2, 4, 6), tail=True),
+    dict(name="rng_shipped_mid", weights="shipped", images=("rng", 1), n=8, shifts=(7, 10, 11), dump=True, tail=True),
+    dict(name="rng_random_mid", weights=("rng", 7), images=("rng", 2), n=4, shifts=(9, 12, 13), dump=True, tail=True),
+    dict(name="shipped_shift0", weights="shipped", images=("rng", 3), n=2, shifts=(0, 0, 0)),
+    dict(name="shipped_shift31", weights="shipped", images=("rng", 4), n=2, shifts=(31, 31, 31)),
+    dict(name="smooth_shipped", weights="shipped", images=("smooth", 5), n=6, shifts=(6, 9, 10), tail=True),
+    dict(name="smooth_random", weights=("rng", 11), images=("smooth", 6), n=4, shifts=(8, 12, 13), tail=True),
+    dict(name="max_pos_weights", weights=("const", 0x7F), images=("const", 255), n=1, shifts=(11, 14, 15)),
+    dict(name="min_neg_weights", weights=("const", 0x80), images=("rng", 8), n=1, shifts=(0, 0, 0)),
+    dict(name="sparse_weights", weights=("sparse", 9), images=("rng", 10), n=3, shifts=(5, 7, 8), tail=True),
+    dict(name="mixed_shifts", weights=("rng", 12), images=("smooth", 13), n=3, shifts=(3, 13, 9)),
+]
+
+# generic H x W cases (oracle = arm_benchmark.arm_conv_layer; arm_cnn.c is 128x128 only)
+HW_CASES = [
+    dict(name="hw_256x256", weights="shipped", images=("rng", 20), H=256, W=256, shifts=(7, 10, 11)),
+    dict(name="hw_64x32", weights=("rng", 21), images=("rng", 22), H=64, W=32, shifts=(9, 12, 13)),
+    dict(name="hw_512x512", weights="shipped", images=("smooth", 23), H=512, W=512, shifts=(6, 9, 10)),
+]
