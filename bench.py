@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the conv-stack hot path on B200 (driver contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one pass of the conv stack (128x128 u8 -> 64x16x16 u8, shipped weights.bin, shifts 2/4/6)
+over one batch of B synthetic images per GPU.  `value` is images/s with the batch already resident in HBM;
+`e2e` is the same call through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).
+N > 1: launched by torchrun, one rank per GPU, batch sharded by rank with no data-path collective (weak
+scaling: B images per GPU); times are CUDA-event times, max over ranks.
+`--impl reference` times the reference's own arm_cnn.c (oracle/_ref, one process per host core because
+its static scratch buffers make it non-re-entrant) on the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+OPS_PER_IMAGE = 2 * 40_108_032          # 2 x MACs, arm_benchmark.py:237 summed over the three layers
+BYTES_PER_IMAGE = 16384 + 16384         # algorithmic HBM traffic: image in + features out
+SHIFTS = (2, 4, 6)
+METRIC = "images/s, bit-exact int8 conv stack (128x128 -> 64x16x16)"
+
+
+# ------------------------------------------------------------------------------------------------
+# pieces that are unit-tested on CPU (tests/test_bench_cpu.py)
+# ------------------------------------------------------------------------------------------------
+def shard_range(n_total, rank, world):
+    """Contiguous range [lo, hi) of a global batch owned by `rank`."""
+    lo = (n_total * rank) // world
+    hi = (n_total * (rank + 1)) // world
+    return lo, hi
+
+
+def reduce_max(value, dist):
+    """MAX over ranks of a python float (identity when torch.distributed is not initialised)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_counts(count, dist):
+    """Gather one integer per rank to every rank (used to total the images processed)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [count]
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([count], dtype=torch.int64, device=dev)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [int(o.item()) for o in out]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            in_region = t_begin <= ts <= t_end + 0.1
+            try:
+                if in_region:
+                    sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            if in_region:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: arm_cnn.c on the host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one private mapping of the reference .so (static buffers => never threads)."""
+    seed, n_images, weights, shifts, seconds = args
+    import oracle
+    lib = oracle.load_ref()
+    kind = "reference"
+    if lib is None:
+        lib, kind = oracle.load_port(), "port"
+    rng = np.random.default_rng(seed)
+    imgs = rng.integers(0, 256, (max(n_images, 1), 128, 128), dtype=np.uint8)
+    infer = (lambda im: oracle.ref_infer(lib, im, weights, shifts)) if kind == "reference" else \
+            (lambda im: oracle.port_infer(lib, im, weights, shifts))
+    infer(imgs[0])                                  # warm the code/data paths
+    done, t0 = 0, time.perf_counter()
+    if seconds is not None:
+        while time.perf_counter() - t0 < seconds:
+            infer(imgs[done % len(imgs)])
+            done += 1
+    else:
+        for i in range(n_images):
+            infer(imgs[i])
+            done += 1
+    return done, time.perf_counter() - t0, kind
+
+
+def cpu_reference_rate(weights, cores, seconds=None, images_per_core=None):
+    """images/s of the reference CPU path over `cores` processes; returns (rate, kind, images, wall_s)."""
+    jobs = [(1000 + c, images_per_core or 8, weights, SHIFTS, seconds) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    rate = sum(d / t for d, t, _ in res)
+    return rate, res[0][2], sum(d for d, _, _ in res), wall
+
+
+def run_reference_arm(args, weights):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_core = 32                                    # bounded sample: cores x 32 images per step
+    for _ in range(args.warmup):
+        cpu_reference_rate(weights, cores, images_per_core=2)
+    rates, total_imgs, t_total = [], 0, 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        rate, kind, imgs, wall = cpu_reference_rate(weights, cores, images_per_core=per_core)
+        rates.append(rate)
+        total_imgs += imgs
+        t_total += imgs / rate
+    value = total_imgs / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8*s8->s32", "data": "synthetic",
+        "config": {"workload": f"conv_stack_128x128 (arm_cnn.c on host CPU, {cores} processes x {per_core} images per step; "
+                               f"same stack/weights/shifts as the GPU arm's batch {args.batch})"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{total_imgs} images, one process per core, gcc -O3 (reference's own flags)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, weights):
+    import torch
+    import torch.distributed as dist
+    import fpga_cnn_b200 as fc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours): no CUDA device; there is no CPU fallback. Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ddist = dist if world > 1 else None
+
+    B = args.batch                                   # images per GPU (weak scaling)
+    acc = fc.CNNAccelerator(device=local)
+    acc.load_weights(weights)
+    acc.set_shifts(*SHIFTS)
+    stream = torch.cuda.Stream(device=local)
+    acc.use_stream(stream.cuda_stream)
+
+    # synthetic device-resident batch: this rank's contiguous shard of a world*B image stream
+    lo, hi = shard_range(B * world, rank, world)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234 + rank)
+    imgs = torch.randint(0, 256, (hi - lo, 128, 128), dtype=torch.uint8, device="cuda", generator=g)
+    feats = torch.empty((hi - lo, 64, 16, 16), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if ddist is not None:
+            ddist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        acc.run_batch(imgs, out=feats, direct=args.direct)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = acc.launch_count
+    barrier()
+    t_begin = time.time()
+    acc.timer_start()
+    for _ in range(args.steps):
+        acc.run_batch(imgs, out=feats, direct=args.direct)
+    ms = acc.timer_stop()
+    barrier()
+    t_end = time.time()
+    launches = acc.launch_count - launches0
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    ms = reduce_max(ms, ddist)
+    total_images = sum(gather_counts(hi - lo, ddist)) * args.steps
+    value = total_images / (ms / 1000.0)
+
+    # ---- end to end through the C ABI with pinned host buffers -------------------------------------
+    Be = min(B, args.e2e_batch)
+    h_imgs = fc.alloc_host((Be, 128, 128), np.uint8)
+    h_feats = fc.alloc_host((Be, 64, 16, 16), np.uint8)
+    h_imgs[:] = imgs[:Be].cpu().numpy()
+    acc.use_stream(None)
+    for _ in range(max(1, min(args.warmup, 3))):
+        acc.run_batch(h_imgs, out=h_feats, direct=args.direct)
+    e2e_steps = max(1, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        acc.run_batch(h_imgs, out=h_feats, direct=args.direct)       # synchronous: returns when feats are on the host
+    e2e_s = reduce_max(time.perf_counter() - t0, ddist)
+    e2e_value = world * Be * e2e_steps / e2e_s
+    ok = bool(np.array_equal(h_feats[:64], feats[:64].cpu().numpy()))
+
+    # ---- secondary measurements (rank 0 only, N = 1): full pipeline, batch-1 latency ---------------
+    extra = {}
+    if world == 1 and not args.quick:
+        import inputs
+        fw, fb = inputs.make_fc()
+        acc.load_classifier(fw, fb)
+        acc.use_stream(stream.cuda_stream)
+        m = min(B, 65536)
+        for _ in range(2):
+            acc.infer_batch(imgs[:m], direct=args.direct)
+        torch.cuda.synchronize()
+        acc.timer_start()
+        for _ in range(3):
+            acc.infer_batch(imgs[:m], direct=args.direct)
+        extra["full_pipeline_images_per_s"] = 3 * m / (acc.timer_stop() / 1000.0)
+        acc.use_stream(None)
+        one = h_imgs[0].copy()
+        lat = []
+        for i in range(300):
+            t0 = time.perf_counter()
+            acc.infer_one(one)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[50:])
+        extra["batch1_latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)]}
+
+    # ---- roofline of the dominant kernel (the conv-stack launch) -------------------------------------
+    peaks = load_peaks()
+    # The conv-stack launch dominates the step (fused path: exactly one launch per step), so its average
+    # launch duration is ms / steps, measured with CUDA events on the launching stream.
+    kernel_ms = ms / args.steps
+    int8_peak = 2.0 * peaks["bf16_tflops"]
+    achieved_tops = (hi - lo) * OPS_PER_IMAGE / (kernel_ms / 1e3) / 1e12
+    roofline = {
+        "bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TOP/s", "frac": achieved_tops / int8_peak,
+        "traffic": None,
+        "peak_note": f"int8 dense peak taken as 2 x {peaks['source']} bf16 burst ({peaks['bf16_tflops']} TF/s); nominal 4500 TOP/s",
+        "algorithmic_ops_per_launch": (hi - lo) * OPS_PER_IMAGE,
+        "hbm_achieved_gbs": (hi - lo) * BYTES_PER_IMAGE / (kernel_ms / 1e3) / 1e9,
+        "hbm_peak_gbs": peaks["hbm_gbs"],
+        "kernel_ms": kernel_ms,
+    }
+
+    if rank == 0:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, kind, n_img, wall = cpu_reference_rate(weights, cores, seconds=2.0)
+            cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
+                   "sample": f"{n_img} images of the same workload in a 2 s window, one process per core, gcc -O3"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8*s8->s32", "data": "synthetic",
+            "config": {"workload": f"conv_stack_128x128_batch{B}_per_gpu (configs[1] stack at the north_star batch)",
+                       "batch_per_gpu": B, "weights": "shipped weights.bin", "shifts": list(SHIFTS),
+                       "kernel_path": "direct per-layer" if args.direct else "fused",
+                       "l2_policy": "inputs larger than L2 (in+out = %d MiB per step)" % ((hi - lo) * BYTES_PER_IMAGE >> 20),
+                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": Be * 16384, "d2h_bytes_per_step": Be * 16384,
+                    "batch": Be, "steps": e2e_steps, "host_buffers": "pinned (cnnacc_alloc_host)", "matches_device_run": ok},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536, help="images per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=32768)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--direct", action="store_true", help="time the generic per-layer kernels instead of the fused one")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    weights = np.fromfile(os.path.join(ROOT, "tests", "golden", "weights.bin"), dtype=np.uint8)
+    if args.impl == "reference":
+        run_reference_arm(args, weights)
+    else:
+        run_ours(args, weights)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,13 @@
+"""B200-native drop-in for the conv-stack hot path of tejasd-24/fpga-cnn-object-detection-accelerator.
+
+128x128 u8 image -> Conv3x3 1->16->32->64 (+ >>shift, ReLU/saturate, 2x2 max-pool each) -> 64x16x16 u8
+features, plus the classifier / CAM tail, behind the reference's own call surface.  Python here is only
+the host-side mirror of the reference's engine objects; the work happens in libcnnacc.so (csrc/).
+"""
+from . import _lib
+from ._lib import build, load
+from .accelerator import (ARMEngine, B200Engine, CNNAccelerator, NAMES, alloc_host, bbox_vec, classify_vec,
+                          load_arm_cnn_lib)
+
+__all__ = ["ARMEngine", "B200Engine", "CNNAccelerator", "NAMES", "alloc_host", "bbox_vec", "classify_vec",
+           "load_arm_cnn_lib", "build", "load", "_lib"]

@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's engine objects, backed by libcnnacc.so on a B200.
+
+Same call surface as the reference (file:line under /root/reference/software/):
+
+  CNNAccelerator      pynq_inference.py:95-286   load_weights / load_image / set_shifts / start_inference /
+                                                 wait_done / read_feature_map / read_layer2_output / write_reg / read_reg
+  B200Engine.run      realtime_detect.py:313-363 FPGAEngine.run(gray128) -> (feat (64,256) u8, conv_ms, read_ms)
+  load_arm_cnn_lib    realtime_detect.py:369-392 returns a CDLL whose cnn_infer is the drop-in GPU symbol, so the
+                                                 reference's ARMEngine.run body works unchanged on it
+  classify_vec        realtime_detect.py:68-82   (idx, name, conf, probs)
+  bbox_vec            realtime_detect.py:85-116  (x1, y1, x2, y2)
+
+plus the batch entry points the reference has no analogue for: run_batch, classify_batch, infer_batch.
+There is no CPU fallback and no simulation mode: without the CUDA library / a B200 the constructor raises.
+"""
+import ctypes
+import os
+import time
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+# constants with the reference's names (pynq_inference.py:61-89, realtime_detect.py:33-37)
+REG_CONTROL, REG_STATUS = 0x00, 0x04
+REG_OUTPUT_CH, REG_OUTPUT_ADDR, REG_OUTPUT_DATA, REG_RELU_SHIFTS = 0x20, 0x24, 0x28, 0x28
+L2_NUM_CHANNELS, L2_SIZE, L2_CH_OFFSET = 64, 256, 48
+SHIFT_L0, SHIFT_L1, SHIFT_L2 = 2, 4, 6
+NUM_WEIGHT_BYTES, NUM_IMAGE_BYTES = 23184, 16384
+IMG, N_CH, FM, CH_OFF = 128, 64, 256, 48
+NAMES = ['airplane', 'cat', 'zebra', 'bus', 'bicycle', 'donut']
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def alloc_host(shape, dtype=np.uint8):
+    """Page-locked host array the copy engines stream from (the role of pynq.allocate, realtime_detect.py:293,301)."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    _lib.check(lib.cnnacc_alloc_host(max(nbytes, 1), ctypes.byref(p)))
+    buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.cnnacc_free_host, ctypes.c_void_p(p.value))
+    return arr
+
+
+class CNNAccelerator:
+    """The accelerator object: load weights.bin, run image(s), read back the 64x16x16 features."""
+
+    def __init__(self, bitstream_path=None, device=0):
+        # bitstream_path is accepted for signature compatibility (pynq_inference.py:98) and ignored:
+        # the "overlay" is libcnnacc.so.
+        self._libc = _lib.load()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._libc.cnnacc_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+        self._out_ch = 0
+        self._out_addr = 0
+        self._n_cls = 0
+        self._finalizer = weakref.finalize(self, self._libc.cnnacc_destroy, self._h)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _check(self, rc):
+        _lib.check(rc, self._h)
+
+    def close(self):
+        self._finalizer()
+
+    @property
+    def launch_count(self):
+        return int(self._libc.cnnacc_launch_count(self._h))
+
+    def use_stream(self, cuda_stream_ptr):
+        """Launch on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""
+        self._check(self._libc.cnnacc_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._libc.cnnacc_synchronize(self._h))
+
+    def timer_start(self):
+        self._check(self._libc.cnnacc_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        self._check(self._libc.cnnacc_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    # -- reference surface: pynq_inference.CNNAccelerator --------------------------------------------
+    def load_weights(self, weights_path):
+        """pynq_inference.py:186-207.  Accepts a path or a 23184-byte array."""
+        weights = np.fromfile(weights_path, dtype=np.uint8) if isinstance(weights_path, (str, os.PathLike)) \
+            else np.ascontiguousarray(weights_path, dtype=np.uint8).reshape(-1)
+        assert len(weights) == NUM_WEIGHT_BYTES, f"Expected {NUM_WEIGHT_BYTES} weights, got {len(weights)}"
+        self._check(self._libc.cnnacc_load_weights(self._h, _vp(weights), weights.size))
+
+    def load_image(self, image):
+        """pynq_inference.py:209-224."""
+        if isinstance(image, (str, os.PathLike)):
+            image = np.fromfile(image, dtype=np.uint8)
+        image = np.ascontiguousarray(image, dtype=np.uint8).reshape(-1)
+        assert len(image) == NUM_IMAGE_BYTES, f"Expected {NUM_IMAGE_BYTES} pixels, got {len(image)}"
+        self._check(self._libc.cnnacc_load_image(self._h, _vp(image), image.size))
+
+    def set_shifts(self, s0=SHIFT_L0, s1=SHIFT_L1, s2=SHIFT_L2):
+        """pynq_inference.py:226-229.  Values outside 0..31 raise ValueError instead of being masked."""
+        self._check(self._libc.cnnacc_set_shifts(self._h, int(s0), int(s1), int(s2)))
+
+    def get_shifts(self):
+        s = (ctypes.c_int * 3)()
+        self._check(self._libc.cnnacc_get_shifts(self._h, s))
+        return tuple(s)
+
+    def start_inference(self):
+        """pynq_inference.py:231-234."""
+        self._check(self._libc.cnnacc_start(self._h))
+
+    def wait_done(self, timeout=10.0):
+        """pynq_inference.py:236-251: returns elapsed seconds, raises TimeoutError."""
+        t0 = time.time()
+        rc = self._libc.cnnacc_wait(self._h, int(timeout * 1e6))
+        if rc == _lib.ERR_TIMEOUT:
+            st = self._libc.cnnacc_status(self._h)
+            raise TimeoutError(f"Timed out after {timeout}s (busy={st & 1}, done={(st >> 1) & 1}, layer={(st >> 2) & 3})")
+        self._check(rc)
+        return time.time() - t0
+
+    def read_feature_map(self, channel, num_values):
+        """pynq_inference.py:253-265 over the 112-channel feature-BRAM map (0-15 L0, 16-47 L1, 48-111 L2)."""
+        values = np.zeros(num_values, dtype=np.uint8)
+        self._check(self._libc.cnnacc_read_feature_map(self._h, int(channel), int(num_values), _vp(values)))
+        return values
+
+    def read_layer2_output(self):
+        """pynq_inference.py:267-286 -> (64, 256) uint8."""
+        features = np.zeros((L2_NUM_CHANNELS, L2_SIZE), dtype=np.uint8)
+        self._check(self._libc.cnnacc_read_features(self._h, _vp(features), L2_NUM_CHANNELS, L2_CH_OFFSET))
+        return features
+
+    def write_reg(self, offset, value):
+        """Register-file view used by dump_fpga_features.py:42-88 (writes 0x20/0x24, reads 0x28)."""
+        value = int(value)
+        if offset == REG_CONTROL:
+            if value & 0x1:
+                self.start_inference()
+        elif offset == REG_OUTPUT_CH:
+            self._out_ch = value & 0x7F
+        elif offset == REG_OUTPUT_ADDR:
+            self._out_addr = value & 0xFFF
+        elif offset == REG_RELU_SHIFTS:
+            self.set_shifts(value & 0x1F, (value >> 5) & 0x1F, (value >> 10) & 0x1F)
+
+    def read_reg(self, offset):
+        if offset == REG_STATUS:
+            st = self._libc.cnnacc_status(self._h)
+            if st < 0:
+                self._check(st)
+            return st
+        if offset == REG_OUTPUT_DATA:
+            depth = 4096 if self._out_ch < 16 else (1024 if self._out_ch < 48 else 256)
+            if self._out_ch >= 112 or self._out_addr >= depth:
+                return 0
+            return int(self.read_feature_map(self._out_ch, self._out_addr + 1)[self._out_addr])
+        return 0
+
+    # -- batch entry points -----------------------------------------------------------------------
+    def run_batch(self, images, out=None, direct=False):
+        """images [N,H,W] u8 (numpy, host) or a torch CUDA tensor -> features [N,64,H/8,W/8] u8 of the same kind."""
+        flags = _lib.FLAG_DIRECT if direct else 0
+        if _is_torch_cuda(images):
+            import torch
+            assert images.dtype == torch.uint8 and images.is_contiguous() and images.dim() == 3
+            n, H, W = images.shape
+            if out is None:
+                out = torch.empty((n, 64, H // 8, W // 8), dtype=torch.uint8, device=images.device)
+            self._check(self._libc.cnnacc_run_batch(self._h, ctypes.c_void_p(images.data_ptr()), n, H, W,
+                                                    ctypes.c_void_p(out.data_ptr()), flags | _lib.FLAG_DEVICE_PTRS))
+            return out
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        if images.ndim != 3:
+            raise ValueError("images must be [N,H,W]")
+        n, H, W = images.shape
+        if out is None:
+            out = np.empty((n, 64, H // 8, W // 8), dtype=np.uint8)
+        self._check(self._libc.cnnacc_run_batch(self._h, _vp(images), n, H, W, _vp(out), flags))
+        return out
+
+    def load_classifier(self, fc_w, fc_b):
+        fc_w = np.ascontiguousarray(fc_w, dtype=np.float32)
+        fc_b = np.ascontiguousarray(fc_b, dtype=np.float32)
+        if fc_w.ndim != 2 or fc_w.shape[1] != 1024 or fc_b.shape != (fc_w.shape[0],):
+            raise ValueError(f"classifier must be (n_cls,1024)+(n_cls,), got {fc_w.shape} {fc_b.shape}")
+        self._check(self._libc.cnnacc_load_classifier(self._h, _vp(fc_w), _vp(fc_b), fc_w.shape[0]))
+        self._n_cls = fc_w.shape[0]
+
+    def _predict(self, fn, x, direct=False):
+        flags = _lib.FLAG_DIRECT if direct else 0
+        if self._n_cls == 0:
+            raise RuntimeError("classifier not loaded")
+        if _is_torch_cuda(x):
+            import torch
+            n = x.shape[0]
+            probs = torch.empty((n, self._n_cls), dtype=torch.float32, device=x.device)
+            cls = torch.empty((n,), dtype=torch.int32, device=x.device)
+            bbox = torch.empty((n, 4), dtype=torch.int32, device=x.device)
+            self._check(fn(self._h, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(probs.data_ptr()),
+                           ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(bbox.data_ptr()),
+                           flags | _lib.FLAG_DEVICE_PTRS))
+            return cls, probs, bbox
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        n = x.shape[0]
+        if x[0].size != 16384:
+            raise ValueError("expected [N,128,128] images or [N,64,256] features")
+        probs = np.empty((n, self._n_cls), dtype=np.float32)
+        cls = np.empty((n,), dtype=np.int32)
+        bbox = np.empty((n, 4), dtype=np.int32)
+        self._check(fn(self._h, _vp(x), n, _vp(probs), _vp(cls), _vp(bbox), flags))
+        return cls, probs, bbox
+
+    def classify_batch(self, features):
+        """features [N,64,256] (or [N,64,16,16]) u8 -> (cls [N] i32, probs [N,n_cls] f32, bbox [N,4] i32)."""
+        return self._predict(self._libc.cnnacc_classify_batch, features)
+
+    def bbox_batch(self, features, cls):
+        """bbox_vec for given classes: features [N,64,256] u8 + cls [N] i32 -> bbox [N,4] i32 (host arrays)."""
+        if self._n_cls == 0:
+            raise RuntimeError("classifier not loaded")
+        x = np.ascontiguousarray(features, dtype=np.uint8)
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        n = x.shape[0]
+        if x[0].size != 16384 or cls.shape != (n,):
+            raise ValueError("expected [N,64,256] features and [N] classes")
+        bbox = np.empty((n, 4), dtype=np.int32)
+        self._check(self._libc.cnnacc_classify_batch(self._h, _vp(x), n, None, _vp(cls), _vp(bbox), _lib.FLAG_CLS_GIVEN))
+        return bbox
+
+    def infer_batch(self, images, direct=False):
+        """images [N,128,128] u8 -> (cls, probs, bbox); features never leave the GPU."""
+        return self._predict(self._libc.cnnacc_infer_batch, images, direct)
+
+    def infer_one(self, gray128):
+        """One image, lowest latency.  -> (feat (64,256) u8, conv_ms, read_ms)."""
+        img = np.ascontiguousarray(gray128, dtype=np.uint8).reshape(-1)
+        assert img.size == NUM_IMAGE_BYTES
+        feat = np.empty(N_CH * FM, dtype=np.uint8)
+        c, r = ctypes.c_float(), ctypes.c_float()
+        self._check(self._libc.cnnacc_infer_one(self._h, _vp(img), _vp(feat), ctypes.byref(c), ctypes.byref(r)))
+        return feat.reshape(N_CH, FM), c.value, r.value
+
+
+class B200Engine:
+    """FPGAEngine's surface (realtime_detect.py:246-363): run(gray128) -> (feat, conv_ms, read_ms)."""
+
+    def __init__(self, weights=None, shifts=(SHIFT_L0, SHIFT_L1, SHIFT_L2), device=0, clib=None):
+        self.acc = CNNAccelerator(device=device)
+        if weights is not None:
+            self.acc.load_weights(weights)
+        self.acc.set_shifts(*shifts)
+
+    def run(self, gray128):
+        feat, conv_ms, read_ms = self.acc.infer_one(np.asarray(gray128).flatten().astype(np.uint8))
+        return feat.copy(), conv_ms, read_ms
+
+
+def load_arm_cnn_lib():
+    """realtime_detect.py:369-392: a CDLL exposing cnn_infer with argtypes=[c_void_p]*4 -- here the GPU symbol."""
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.cnn_infer.argtypes = [ctypes.c_void_p] * 4
+    lib.cnn_infer.restype = ctypes.c_int
+    return lib
+
+
+class ARMEngine:
+    """realtime_detect.py:398-436 with the C library swapped for libcnnacc.so; run() body follows the reference."""
+
+    def __init__(self, weights_bin, shifts=(SHIFT_L0, SHIFT_L1, SHIFT_L2)):
+        self.wt = np.fromfile(weights_bin, dtype=np.uint8) if isinstance(weights_bin, (str, os.PathLike)) \
+            else np.ascontiguousarray(weights_bin, dtype=np.uint8)
+        self.shifts_arr = np.array(shifts, dtype=np.int32)
+        self.output_buf = np.zeros(N_CH * FM, dtype=np.uint8)
+        self.clib = load_arm_cnn_lib()
+
+    def run(self, gray128):
+        img = np.asarray(gray128).flatten().astype(np.uint8)
+        t0 = time.time()
+        rc = self.clib.cnn_infer(img.ctypes.data_as(ctypes.c_void_p), self.wt.ctypes.data_as(ctypes.c_void_p),
+                                 self.shifts_arr.ctypes.data_as(ctypes.c_void_p),
+                                 self.output_buf.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"cnn_infer returned {rc}")
+        conv_ms = (time.time() - t0) * 1000
+        return self.output_buf.reshape(N_CH, FM).copy(), conv_ms, 0.0
+
+
+_tail_acc = {}
+
+
+def _tail_accelerator(fc_w, fc_b, device=0):
+    key = (device, fc_w.shape, fc_w.tobytes(), fc_b.tobytes())
+    acc = _tail_acc.get("acc")
+    if acc is None:
+        acc = _tail_acc["acc"] = CNNAccelerator(device=device)
+    if _tail_acc.get("key") != key:
+        acc.load_classifier(fc_w, fc_b)
+        _tail_acc["key"] = key
+    return acc
+
+
+def classify_vec(feat_flat, fc_w, fc_b, names=NAMES):
+    """realtime_detect.py:68-82 on the GPU: (64,256) u8 -> (idx, name, conf, probs)."""
+    fc_w = np.ascontiguousarray(fc_w, dtype=np.float32)
+    fc_b = np.ascontiguousarray(fc_b, dtype=np.float32)
+    acc = _tail_accelerator(fc_w, fc_b)
+    cls, probs, _ = acc.classify_batch(np.asarray(feat_flat, dtype=np.uint8).reshape(1, 64, 256))
+    i = int(cls[0])
+    return i, names[i], float(probs[0, i]), probs[0]
+
+
+def bbox_vec(feat_flat, cls_idx, fc_w, fc_b=None):
+    """realtime_detect.py:85-116 on the GPU: bbox of the CAM of class cls_idx."""
+    fc_w = np.ascontiguousarray(fc_w, dtype=np.float32)
+    fc_b = np.zeros(fc_w.shape[0], np.float32) if fc_b is None else np.ascontiguousarray(fc_b, dtype=np.float32)
+    acc = _tail_accelerator(fc_w, fc_b)
+    feats = np.ascontiguousarray(feat_flat, dtype=np.uint8).reshape(1, 64, 256)
+    bbox = acc.bbox_batch(feats, np.array([cls_idx], dtype=np.int32))
+    return tuple(int(v) for v in bbox[0])

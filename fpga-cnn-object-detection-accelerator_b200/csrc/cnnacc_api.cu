@@ -1,0 +1,540 @@
+// cnnacc_api.cu -- the C ABI of include/cnnacc.h: handle, host logic, launches.  No CPU compute path.
+#include "../../include/cnnacc.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "conv_direct.cuh"
+#include "conv_fused.cuh"
+#include "tail.cuh"
+#include "weights_pack.h"
+
+using namespace cnnacc;
+
+namespace {
+
+constexpr int kSlots = 3;                       // H2D / compute / D2H overlap for host-pointer batches
+constexpr size_t kBramBytes = 16 * 4096 + 32 * 1024 + 64 * 256;   // 112-channel feature-BRAM mirror
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    float* d_probs = nullptr; int32_t* d_cls = nullptr; int32_t* d_bbox = nullptr;
+    size_t cap_in = 0, cap_out = 0, cap_pred = 0;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct cnnacc_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_done = nullptr;
+    int sm_count = 0;
+    bool weights_loaded = false, fc_loaded = false;
+    int shifts[3] = {2, 4, 6};                  // SHIFT_L0..2 defaults, pynq_inference.py:83-85
+    uint8_t wbin[CNNACC_WEIGHT_BYTES];
+    // device-side weights
+    uint32_t* d_wdirect = nullptr; size_t wdirect_off[3] = {0, 0, 0};
+    FusedWeights fused;                         // packed operands of the fused kernel (conv_fused.cuh)
+    float *d_fcw = nullptr, *d_fcb = nullptr; int n_cls = 0;
+    // workspaces (grown on demand) for the per-layer path and for infer_batch
+    uint8_t *d_l0 = nullptr, *d_l1 = nullptr, *d_feat = nullptr;
+    size_t cap_l0 = 0, cap_l1 = 0, cap_feat = 0;
+    Slot slots[kSlots];
+    // single-image protocol state
+    uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned
+    uint8_t *d_img1 = nullptr, *d_bram = nullptr;
+    bool image_loaded = false, started = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(cnnacc_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail((h), CNNACC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int grow(cnnacc_handle* h, uint8_t** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) CU(h, cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    CU(h, cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+bool valid_hw(int H, int W) { return H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && H <= 8192 && W <= 8192; }
+
+// One layer of the generic per-layer path on `stream`.
+int launch_direct_layer(cnnacc_handle* h, cudaStream_t stream, int layer, const uint8_t* in, uint8_t* out,
+                        int64_t n, int H, int W) {
+    const int tiles_x = (W + kDirTile - 1) / kDirTile, tiles_y = (H + kDirTile - 1) / kDirTile;
+    dim3 grid((unsigned)n, (unsigned)(tiles_x * tiles_y), (unsigned)(kLayers[layer].oc / kDirOcb));
+    conv3x3_pool_direct_kernel<<<grid, 256, 0, stream>>>(in, out, h->d_wdirect + h->wdirect_off[layer],
+                                                         kLayers[layer].ic, kLayers[layer].oc, H, W,
+                                                         h->shifts[layer], tiles_x);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+// Conv stack for n device-resident images on `stream`.  l0/l1 are workspaces for the per-layer path.
+int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_imgs, int64_t n, int H, int W,
+                      uint8_t* d_feats, uint32_t flags, uint8_t* d_l0, uint8_t* d_l1) {
+    const bool fused_ok = (H == CNNACC_IMG && W == CNNACC_IMG) && !(flags & CNNACC_FLAG_DIRECT) && h->fused.ready;
+    if (fused_ok) {
+        int rc = launch_fused(h->fused, stream, d_imgs, n, d_feats, h->shifts, h->sm_count,
+                              (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l0 : nullptr,
+                              (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l1 : nullptr);
+        h->launches++;
+        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+        return 0;
+    }
+    int rc;
+    if ((rc = launch_direct_layer(h, stream, 0, d_imgs, d_l0, n, H, W))) return rc;
+    if ((rc = launch_direct_layer(h, stream, 1, d_l0, d_l1, n, H / 2, W / 2))) return rc;
+    if ((rc = launch_direct_layer(h, stream, 2, d_l1, d_feats, n, H / 4, W / 4))) return rc;
+    return 0;
+}
+
+bool needs_maps(const cnnacc_handle* h, int H, int W, uint32_t flags) {
+    const bool fused_ok = (H == CNNACC_IMG && W == CNNACC_IMG) && !(flags & CNNACC_FLAG_DIRECT) && h->fused.ready;
+    return !fused_ok || (flags & CNNACC_FLAG_KEEP_MAPS);
+}
+
+// images per chunk so that the per-layer workspaces stay around 512 MiB
+int64_t chunk_images(int H, int W) {
+    const size_t per = (size_t)H * W * 8;
+    return (int64_t)std::max<size_t>(1, ((size_t)512 << 20) / per);
+}
+
+int ensure_maps(cnnacc_handle* h, int64_t n, int H, int W) {
+    int rc;
+    if ((rc = grow(h, &h->d_l0, &h->cap_l0, (size_t)n * 16 * (H / 2) * (W / 2)))) return rc;
+    if ((rc = grow(h, &h->d_l1, &h->cap_l1, (size_t)n * 32 * (H / 4) * (W / 4)))) return rc;
+    return 0;
+}
+
+int launch_tail(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, int64_t n, float* d_probs,
+                int32_t* d_cls, int32_t* d_bbox, bool cls_given = false) {
+    if (n == 0) return 0;
+    classify_bbox_kernel<<<(unsigned)n, 256, 0, stream>>>(d_feats, h->d_fcw, h->d_fcb, h->n_cls, d_probs, d_cls, d_bbox,
+                                                          cls_given ? d_cls : nullptr);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+int slot_reserve(cnnacc_handle* h, Slot& s, size_t in_bytes, size_t out_bytes, size_t n_pred) {
+    int rc;
+    if ((rc = grow(h, &s.d_in, &s.cap_in, in_bytes))) return rc;
+    if ((rc = grow(h, &s.d_out, &s.cap_out, out_bytes))) return rc;
+    if (n_pred > s.cap_pred) {
+        if (s.d_probs) cudaFree(s.d_probs);
+        if (s.d_cls) cudaFree(s.d_cls);
+        if (s.d_bbox) cudaFree(s.d_bbox);
+        s.d_probs = nullptr; s.d_cls = nullptr; s.d_bbox = nullptr; s.cap_pred = 0;
+        CU(h, cudaMalloc(&s.d_probs, n_pred * kMaxClasses * sizeof(float)));
+        CU(h, cudaMalloc(&s.d_cls, n_pred * sizeof(int32_t)));
+        CU(h, cudaMalloc(&s.d_bbox, n_pred * 4 * sizeof(int32_t)));
+        s.cap_pred = n_pred;
+    }
+    return 0;
+}
+
+int check_ready(cnnacc_handle* h) {
+    if (!h) return CNNACC_ERR_ARG;
+    if (!h->weights_loaded) return fail(h, CNNACC_ERR_STATE, "weights not loaded (call cnnacc_load_weights)");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnnacc_create(int device_id, cnnacc_handle** out) {
+    if (!out) return fail(nullptr, CNNACC_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CNNACC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                  " (this library has no CPU fallback)");
+    if (device_id < 0 || device_id >= count) return fail(nullptr, CNNACC_ERR_ARG, "device_id out of range");
+    cnnacc_handle* h = new cnnacc_handle();
+    h->device = device_id;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete h;
+        return CNNACC_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; this library is built for sm_100a (B200) only";
+        delete h;
+        return CNNACC_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->stream = h->own_stream;
+    cudaEvent_t* evs[] = {&h->ev_t0, &h->ev_t1, &h->ev_a, &h->ev_b, &h->ev_c, &h->ev_done};
+    for (auto ev : evs)
+        if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (auto& s : h->slots)
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaHostAlloc(&h->h_img, CNNACC_IMG * CNNACC_IMG, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaMalloc(&h->d_img1, CNNACC_IMG * CNNACC_IMG)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_bram, kBramBytes)) != cudaSuccess) return bail("cudaMalloc", e);
+    *out = h;
+    return CNNACC_OK;
+}
+
+int cnnacc_destroy(cnnacc_handle* h) {
+    if (!h) return CNNACC_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& s : h->slots) {
+        cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_probs); cudaFree(s.d_cls); cudaFree(s.d_bbox);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(h->d_wdirect); cudaFree(h->d_fcw); cudaFree(h->d_fcb);
+    cudaFree(h->d_l0); cudaFree(h->d_l1); cudaFree(h->d_feat); cudaFree(h->d_img1); cudaFree(h->d_bram);
+    fused_free(h->fused);
+    cudaFreeHost(h->h_img); cudaFreeHost(h->h_bram);
+    cudaEvent_t evs[] = {h->ev_t0, h->ev_t1, h->ev_a, h->ev_b, h->ev_c, h->ev_done};
+    for (auto ev : evs) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return CNNACC_OK;
+}
+
+int cnnacc_set_stream(cnnacc_handle* h, void* cuda_stream) {
+    if (!h) return CNNACC_ERR_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return CNNACC_OK;
+}
+
+const char* cnnacc_last_error(const cnnacc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t cnnacc_launch_count(const cnnacc_handle* h) { return h ? h->launches : 0; }
+
+int cnnacc_load_weights(cnnacc_handle* h, const uint8_t* weights_bin, size_t n) {
+    if (!h || !weights_bin) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (n != CNNACC_WEIGHT_BYTES)
+        return fail(h, CNNACC_ERR_ARG, "Expected 23184 weights, got " + std::to_string(n));   // pynq_inference.py:189
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());      // weights may be in use by queued launches
+    std::memcpy(h->wbin, weights_bin, n);
+    std::vector<uint32_t> packed;
+    pack_direct_weights(h->wbin, packed, h->wdirect_off);
+    if (!h->d_wdirect) CU(h, cudaMalloc(&h->d_wdirect, packed.size() * sizeof(uint32_t)));
+    CU(h, cudaMemcpy(h->d_wdirect, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    int rc = fused_load_weights(h->fused, h->wbin);
+    if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused_load_weights: ") + cudaGetErrorString((cudaError_t)rc));
+    h->weights_loaded = true;
+    return CNNACC_OK;
+}
+
+int cnnacc_set_shifts(cnnacc_handle* h, int s0, int s1, int s2) {
+    if (!h) return CNNACC_ERR_ARG;
+    const int s[3] = {s0, s1, s2};
+    for (int v : s)
+        if (v < 0 || v > 31) return fail(h, CNNACC_ERR_ARG, "shift outside 0..31: " + std::to_string(v));
+    std::memcpy(h->shifts, s, sizeof(s));
+    return CNNACC_OK;
+}
+
+int cnnacc_get_shifts(const cnnacc_handle* h, int* s3) {
+    if (!h || !s3) return CNNACC_ERR_ARG;
+    std::memcpy(s3, h->shifts, sizeof(h->shifts));
+    return CNNACC_OK;
+}
+
+int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, int W, uint8_t* feats, uint32_t flags) {
+    int rc;
+    if ((rc = check_ready(h))) return rc;
+    if (n < 0 || !valid_hw(H, W)) return fail(h, CNNACC_ERR_ARG, "bad n / H / W (H, W must be multiples of 16)");
+    if (n == 0) return CNNACC_OK;
+    if (!imgs || !feats) return fail(h, CNNACC_ERR_ARG, "NULL image / feature pointer");
+    CU(h, cudaSetDevice(h->device));
+    const size_t in_sz = (size_t)H * W, out_sz = (size_t)64 * (H / 8) * (W / 8);
+    const bool maps = needs_maps(h, H, W, flags);
+    const int64_t chunk = maps ? std::min<int64_t>(n, chunk_images(H, W)) : n;
+
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        if (maps && (rc = ensure_maps(h, chunk, H, W))) return rc;
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t m = std::min(chunk, n - i0);
+            if ((rc = conv_stack_device(h, h->stream, imgs + i0 * in_sz, m, H, W, feats + i0 * out_sz, flags, h->d_l0, h->d_l1)))
+                return rc;
+        }
+        return CNNACC_OK;
+    }
+
+    // host pointers: 3-slot pipeline, slot streams overlap H2D / kernels / D2H
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), ((size_t)64 << 20) / in_sz)));
+    if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
+        const int64_t m = std::min(hchunk, n - i0);
+        Slot& s = h->slots[ci % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
+        if (maps && ci > 0) CU(h, cudaStreamWaitEvent(s.stream, h->ev_c, 0));   // shared l0/l1 workspace: serialise compute
+        CU(h, cudaMemcpyAsync(s.d_in, imgs + i0 * in_sz, m * in_sz, cudaMemcpyHostToDevice, s.stream));
+        if ((rc = conv_stack_device(h, s.stream, s.d_in, m, H, W, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+        if (maps) CU(h, cudaEventRecord(h->ev_c, s.stream));
+        CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    return CNNACC_OK;
+}
+
+int cnnacc_load_image(cnnacc_handle* h, const uint8_t* img, size_t n) {
+    if (!h || !img) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (n != (size_t)CNNACC_IMG * CNNACC_IMG)
+        return fail(h, CNNACC_ERR_ARG, "Expected 16384 pixels, got " + std::to_string(n));     // pynq_inference.py:214
+    CU(h, cudaSetDevice(h->device));
+    if (h->started) CU(h, cudaEventSynchronize(h->ev_done));   // s_axis_tready = !busy (…S00_AXI.v:390)
+    std::memcpy(h->h_img, img, n);
+    h->image_loaded = true;
+    return CNNACC_OK;
+}
+
+int cnnacc_start(cnnacc_handle* h) {
+    int rc;
+    if ((rc = check_ready(h))) return rc;
+    if (!h->image_loaded) return fail(h, CNNACC_ERR_STATE, "no image loaded (call cnnacc_load_image)");
+    CU(h, cudaSetDevice(h->device));
+    uint8_t *l0 = h->d_bram, *l1 = h->d_bram + 16 * 4096, *l2 = l1 + 32 * 1024;
+    CU(h, cudaMemcpyAsync(h->d_img1, h->h_img, CNNACC_IMG * CNNACC_IMG, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = conv_stack_device(h, h->stream, h->d_img1, 1, CNNACC_IMG, CNNACC_IMG, l2, CNNACC_FLAG_KEEP_MAPS, l0, l1))) return rc;
+    CU(h, cudaMemcpyAsync(h->h_bram, h->d_bram, kBramBytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev_done, h->stream));
+    h->started = true;
+    return CNNACC_OK;
+}
+
+int cnnacc_status(cnnacc_handle* h) {
+    if (!h) return CNNACC_ERR_ARG;
+    if (!h->started) return 0;                               // idle: busy=0 done=0
+    cudaError_t e = cudaEventQuery(h->ev_done);
+    if (e == cudaSuccess) return 0x2 | (2 << 2);             // done, current_layer = 2
+    if (e == cudaErrorNotReady) return 0x1;                  // busy
+    return fail(h, CNNACC_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+}
+
+int cnnacc_wait(cnnacc_handle* h, int timeout_us) {
+    if (!h) return CNNACC_ERR_ARG;
+    if (!h->started) return fail(h, CNNACC_ERR_STATE, "wait without start");
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        cudaError_t e = cudaEventQuery(h->ev_done);
+        if (e == cudaSuccess) return CNNACC_OK;
+        if (e != cudaErrorNotReady) return fail(h, CNNACC_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (us > timeout_us) return fail(h, CNNACC_ERR_TIMEOUT, "timed out waiting for done");   // fast_readout.c:91
+    }
+}
+
+int cnnacc_read_feature_map(cnnacc_handle* h, int channel, int num_values, uint8_t* out) {
+    if (!h || !out) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (!h->started) return fail(h, CNNACC_ERR_STATE, "no inference has been started");
+    if (channel < 0 || channel >= CNNACC_BRAM_CHANNELS) return fail(h, CNNACC_ERR_ARG, "channel outside 0..111");
+    CU(h, cudaEventSynchronize(h->ev_done));
+    size_t off, depth;
+    if (channel < 16)      { off = (size_t)channel * 4096;                       depth = 4096; }
+    else if (channel < 48) { off = 16 * 4096 + (size_t)(channel - 16) * 1024;    depth = 1024; }
+    else                   { off = 16 * 4096 + 32 * 1024 + (size_t)(channel - 48) * 256; depth = 256; }
+    if (num_values < 0 || (size_t)num_values > depth) return fail(h, CNNACC_ERR_ARG, "num_values exceeds the channel's BRAM depth");
+    std::memcpy(out, h->h_bram + off, (size_t)num_values);
+    return CNNACC_OK;
+}
+
+int cnnacc_read_features(cnnacc_handle* h, uint8_t* out, int n_ch, int ch_off) {
+    if (!h || !out) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (n_ch < 0 || ch_off < 0 || ch_off + n_ch > CNNACC_BRAM_CHANNELS) return fail(h, CNNACC_ERR_ARG, "channel range outside 0..111");
+    for (int c = 0; c < n_ch; c++) {                        // read_features_full reads 256 values per channel
+        int rc = cnnacc_read_feature_map(h, ch_off + c, 256, out + (size_t)c * 256);
+        if (rc) return rc;
+    }
+    return CNNACC_OK;
+}
+
+int cnnacc_infer_one(cnnacc_handle* h, const uint8_t* img, uint8_t* feat, float* conv_ms, float* read_ms) {
+    int rc;
+    if ((rc = check_ready(h))) return rc;
+    if (!img || !feat) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    CU(h, cudaSetDevice(h->device));
+    if (h->started) CU(h, cudaEventSynchronize(h->ev_done));
+    const bool maps = needs_maps(h, CNNACC_IMG, CNNACC_IMG, 0);
+    uint8_t *l0 = h->d_bram, *l1 = h->d_bram + 16 * 4096, *l2 = l1 + 32 * 1024;
+    std::memcpy(h->h_img, img, CNNACC_FEAT_BYTES);
+    CU(h, cudaMemcpyAsync(h->d_img1, h->h_img, CNNACC_IMG * CNNACC_IMG, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaEventRecord(h->ev_a, h->stream));
+    if ((rc = conv_stack_device(h, h->stream, h->d_img1, 1, CNNACC_IMG, CNNACC_IMG, l2, 0, maps ? l0 : nullptr, maps ? l1 : nullptr))) return rc;
+    CU(h, cudaEventRecord(h->ev_b, h->stream));
+    uint8_t* h_l2 = h->h_bram + 16 * 4096 + 32 * 1024;
+    CU(h, cudaMemcpyAsync(h_l2, l2, CNNACC_FEAT_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev_c, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(feat, h_l2, CNNACC_FEAT_BYTES);
+    if (conv_ms) CU(h, cudaEventElapsedTime(conv_ms, h->ev_a, h->ev_b));
+    if (read_ms) CU(h, cudaEventElapsedTime(read_ms, h->ev_b, h->ev_c));
+    return CNNACC_OK;
+}
+
+int cnnacc_load_classifier(cnnacc_handle* h, const float* fc_w, const float* fc_b, int n_cls) {
+    if (!h || !fc_w || !fc_b) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (n_cls < 1 || n_cls > kMaxClasses) return fail(h, CNNACC_ERR_ARG, "n_cls outside 1..16");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    if (!h->d_fcw) CU(h, cudaMalloc(&h->d_fcw, (size_t)kMaxClasses * 1024 * sizeof(float)));
+    if (!h->d_fcb) CU(h, cudaMalloc(&h->d_fcb, kMaxClasses * sizeof(float)));
+    CU(h, cudaMemcpy(h->d_fcw, fc_w, (size_t)n_cls * 1024 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_fcb, fc_b, n_cls * sizeof(float), cudaMemcpyHostToDevice));
+    h->n_cls = n_cls;
+    h->fc_loaded = true;
+    return CNNACC_OK;
+}
+
+// shared body of classify_batch / infer_batch
+static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool src_is_images,
+                        float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
+    int rc;
+    if (!h) return CNNACC_ERR_ARG;
+    if (src_is_images && (rc = check_ready(h))) return rc;
+    if (!h->fc_loaded) return fail(h, CNNACC_ERR_STATE, "classifier not loaded (call cnnacc_load_classifier)");
+    if (n < 0) return fail(h, CNNACC_ERR_ARG, "negative n");
+    if (n == 0) return CNNACC_OK;
+    if (!src) return fail(h, CNNACC_ERR_ARG, "NULL input pointer");
+    CU(h, cudaSetDevice(h->device));
+    const size_t img_sz = CNNACC_FEAT_BYTES;        // 128*128 image and 64*256 feature map are both 16 KiB
+    const int nc = h->n_cls;
+    const bool maps = src_is_images && needs_maps(h, CNNACC_IMG, CNNACC_IMG, flags);
+    const bool cls_given = (flags & CNNACC_FLAG_CLS_GIVEN) != 0;
+    if (cls_given && !cls) return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_CLS_GIVEN without a cls array");
+
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        const int64_t chunk = std::min<int64_t>(n, 16384);
+        if (src_is_images) {
+            if ((rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)chunk * img_sz))) return rc;
+            if (maps && (rc = ensure_maps(h, chunk, CNNACC_IMG, CNNACC_IMG))) return rc;
+        }
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t m = std::min(chunk, n - i0);
+            const uint8_t* f = src + i0 * img_sz;
+            if (src_is_images) {
+                if ((rc = conv_stack_device(h, h->stream, src + i0 * img_sz, m, CNNACC_IMG, CNNACC_IMG, h->d_feat, flags, h->d_l0, h->d_l1))) return rc;
+                f = h->d_feat;
+            }
+            if ((rc = launch_tail(h, h->stream, f, m, probs ? probs + i0 * nc : nullptr, cls ? cls + i0 : nullptr,
+                                  bbox ? bbox + i0 * 4 : nullptr, cls_given))) return rc;
+        }
+        return CNNACC_OK;
+    }
+
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int64_t hchunk = std::min<int64_t>(n, 4096);
+    if (maps && (rc = ensure_maps(h, hchunk, CNNACC_IMG, CNNACC_IMG))) return rc;
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
+        const int64_t m = std::min(hchunk, n - i0);
+        Slot& s = h->slots[ci % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * img_sz, src_is_images ? hchunk * img_sz : 0, hchunk))) return rc;
+        if (maps && ci > 0) CU(h, cudaStreamWaitEvent(s.stream, h->ev_c, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, src + i0 * img_sz, m * img_sz, cudaMemcpyHostToDevice, s.stream));
+        const uint8_t* f = s.d_in;
+        if (src_is_images) {
+            if ((rc = conv_stack_device(h, s.stream, s.d_in, m, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+            if (maps) CU(h, cudaEventRecord(h->ev_c, s.stream));
+            f = s.d_out;
+        }
+        if (cls_given) CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
+        if ((rc = launch_tail(h, s.stream, f, m, s.d_probs, s.d_cls, s.d_bbox, cls_given))) return rc;
+        if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (cls && !cls_given) CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    return CNNACC_OK;
+}
+
+int cnnacc_classify_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
+    return predict_impl(h, feats, n, false, probs, cls, bbox, flags);
+}
+
+int cnnacc_infer_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
+    return predict_impl(h, imgs, n, true, probs, cls, bbox, flags);
+}
+
+int cnnacc_alloc_host(size_t bytes, void** out) {
+    if (!out || bytes == 0) return CNNACC_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return CNNACC_ERR_CUDA; }
+    return CNNACC_OK;
+}
+
+int cnnacc_free_host(void* p) {
+    if (!p) return CNNACC_ERR_ARG;
+    return cudaFreeHost(p) == cudaSuccess ? CNNACC_OK : CNNACC_ERR_CUDA;
+}
+
+int cnnacc_timer_start(cnnacc_handle* h) {
+    if (!h) return CNNACC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaEventRecord(h->ev_t0, h->stream));
+    return CNNACC_OK;
+}
+
+int cnnacc_timer_stop(cnnacc_handle* h, float* ms) {
+    if (!h || !ms) return CNNACC_ERR_ARG;
+    CU(h, cudaEventRecord(h->ev_t1, h->stream));
+    CU(h, cudaEventSynchronize(h->ev_t1));
+    CU(h, cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+    return CNNACC_OK;
+}
+
+int cnnacc_synchronize(cnnacc_handle* h) {
+    if (!h) return CNNACC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    return CNNACC_OK;
+}
+
+// ---- drop-in for arm_cnn.c:159-162 -------------------------------------------------------------
+static std::mutex g_compat_mutex;
+static cnnacc_handle* g_compat = nullptr;
+
+int cnn_infer(const uint8_t* input_img, const uint8_t* weights_bin, const int* shifts, uint8_t* output) {
+    if (!input_img || !weights_bin || !shifts || !output) return CNNACC_ERR_ARG;
+    std::lock_guard<std::mutex> lock(g_compat_mutex);
+    int rc;
+    if (!g_compat && (rc = cnnacc_create(0, &g_compat))) return rc;
+    if (!g_compat->weights_loaded || std::memcmp(g_compat->wbin, weights_bin, CNNACC_WEIGHT_BYTES) != 0)
+        if ((rc = cnnacc_load_weights(g_compat, weights_bin, CNNACC_WEIGHT_BYTES))) return rc;
+    if ((rc = cnnacc_set_shifts(g_compat, shifts[0], shifts[1], shifts[2]))) return rc;
+    return cnnacc_infer_one(g_compat, input_img, output, nullptr, nullptr);
+}
+
+}  // extern "C"

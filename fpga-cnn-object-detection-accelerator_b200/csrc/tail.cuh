@@ -1,0 +1,160 @@
+// tail.cuh -- follow-on kernel: 4x4 spatial-bin pool -> linear -> softmax -> argmax -> CAM bbox.
+//
+// One CTA (256 threads) per image, reading the 64x16x16 u8 feature map (16 KiB) once from HBM/L2.
+// Reference (all /root/reference/software/realtime_detect.py):
+//   classify_vec :68-82   pooled[ch*16 + r*4 + c] = mean of the 4x4 bin of (feat/255); logits = W.pooled + b;
+//                         softmax; argmax
+//   bbox_vec     :85-116  channels with mean > 250 masked; cam = sum_ch w[cls][ch,bin] * fm (fp32, channel
+//                         order); ReLU; /max; thr = max(percentile70, 0.25); bbox of cam > thr, x8 scaling
+// Numerics:
+//   * bin sums are exact integers; pooled = S / 4080 in one rounding (identical to Classifier.classify's
+//     mean-then-/255, pynq_inference.py:325-334; within 1 ulp of classify_vec's /255-then-mean);
+//   * logits: fp32, fixed summation tree (4 bins per thread, warp shuffle tree, 8 warp partials in order);
+//   * CAM: products and sums rounded separately (no FMA) in channel order 0..63, as numpy's reduction over
+//     the outer axis does, so the bbox integers match bit for bit given the same class;
+//   * percentile(70) of 256 values = index 178.5 -> hi - (hi-lo)*0.5 in fp32 (numpy _lerp with t = 0.5).
+#pragma once
+#include "common.cuh"
+
+namespace cnnacc {
+
+constexpr int kMaxClasses = 16;
+
+__global__ void __launch_bounds__(256)
+classify_bbox_kernel(const uint8_t* __restrict__ feats, const float* __restrict__ fc_w,
+                     const float* __restrict__ fc_b, int n_cls,
+                     float* __restrict__ probs, int32_t* __restrict__ cls_out, int32_t* __restrict__ bbox_out,
+                     const int32_t* __restrict__ cls_in)
+{
+    __shared__ __align__(16) uint8_t s_feat[64 * 256];
+    __shared__ float s_part[8][kMaxClasses];
+    __shared__ float s_cam[256];
+    __shared__ float s_red[8];
+    __shared__ int   s_valid[64];
+    __shared__ int   s_cls;
+    __shared__ float s_lohi[2];
+    __shared__ int   s_box[4];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const size_t img = blockIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(feats + img * 16384);
+
+    // thread t owns channel t/4, bin-row t%4: four 16-byte map rows = 64 contiguous bytes
+    int S[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint4 v = src[t * 4 + r];
+        reinterpret_cast<uint4*>(s_feat)[t * 4 + r] = v;
+        S[0] = __dp4a(v.x, 0x01010101u, (unsigned)S[0]);
+        S[1] = __dp4a(v.y, 0x01010101u, (unsigned)S[1]);
+        S[2] = __dp4a(v.z, 0x01010101u, (unsigned)S[2]);
+        S[3] = __dp4a(v.w, 0x01010101u, (unsigned)S[3]);
+    }
+    // channel mean <= 250  <=>  channel sum <= 64000 (bbox_vec: valid = ch_means <= 250)
+    int chsum = S[0] + S[1] + S[2] + S[3];
+    chsum += __shfl_xor_sync(0xffffffffu, chsum, 1);
+    chsum += __shfl_xor_sync(0xffffffffu, chsum, 2);
+    if ((t & 3) == 0) s_valid[t >> 2] = (chsum <= 250 * 256);
+
+    float pooled[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) pooled[c] = __fdiv_rn((float)S[c], 4080.0f);
+
+    // logits: W row-major [n_cls][1024]; this thread's bins are 4t .. 4t+3
+    for (int k = 0; k < n_cls; k++) {
+        float4 w = reinterpret_cast<const float4*>(fc_w + (size_t)k * 1024)[t];
+        float p = pooled[0] * w.x;
+        p = fmaf(pooled[1], w.y, p);
+        p = fmaf(pooled[2], w.z, p);
+        p = fmaf(pooled[3], w.w, p);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+        if (lane == 0) s_part[warp][k] = p;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        float logit = -INFINITY;
+        if (lane < n_cls) {
+            float a = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; w8++) a += s_part[w8][lane];
+            logit = a + fc_b[lane];
+        }
+        float mx = logit;
+        int arg = lane < n_cls ? lane : 0x7fffffff;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            float om = __shfl_xor_sync(0xffffffffu, mx, off);
+            int   oa = __shfl_xor_sync(0xffffffffu, arg, off);
+            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // first maximum, like np.argmax
+        }
+        float e = lane < n_cls ? expf(logit - mx) : 0.f;
+        float sum = e;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (probs && lane < n_cls) probs[img * n_cls + lane] = __fdiv_rn(e, sum);
+        if (lane == 0) {
+            // bbox_vec takes the class as an argument (realtime_detect.py:85); cls_in carries it when given
+            s_cls = cls_in ? min(max(cls_in[img], 0), n_cls - 1) : arg;
+            if (cls_out && !cls_in) cls_out[img] = arg;
+            s_box[0] = 16; s_box[1] = 16; s_box[2] = -1; s_box[3] = -1;   // min col, min row, max col, max row
+        }
+    }
+    __syncthreads();
+    if (!bbox_out) return;
+
+    // CAM: thread t owns pixel t = (py, px); class weights indexed [ch*16 + (py/4)*4 + px/4]
+    const int py = t >> 4, px = t & 15;
+    const float* wc = fc_w + (size_t)s_cls * 1024 + (py >> 2) * 4 + (px >> 2);
+    float cam = 0.f;
+#pragma unroll 8
+    for (int ch = 0; ch < 64; ch++) {
+        float w = s_valid[ch] ? __ldg(wc + ch * 16) : 0.f;
+        cam = __fadd_rn(cam, __fmul_rn(w, (float)s_feat[ch * 256 + t]));
+    }
+    cam = fmaxf(cam, 0.f);
+
+    float m = cam;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = s_red[0];
+#pragma unroll
+    for (int w8 = 1; w8 < 8; w8++) m = fmaxf(m, s_red[w8]);
+    if (m > 0.f) cam = __fdiv_rn(cam, m);
+    s_cam[t] = cam;
+    __syncthreads();
+
+    // rank by counting (stable on index): sorted[178] and sorted[179] bracket the 70th percentile
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 256; j++) {
+        float v = s_cam[j];
+        rank += (v < cam) || (v == cam && j < t);
+    }
+    if (rank == 178) s_lohi[0] = cam;
+    if (rank == 179) s_lohi[1] = cam;
+    __syncthreads();
+    const float lo = s_lohi[0], hi = s_lohi[1];
+    float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
+    thr = (0.25f > thr) ? 0.25f : thr;                      // python max(p, 0.25)
+    if (cam > thr) {
+        atomicMin(&s_box[0], px); atomicMin(&s_box[1], py);
+        atomicMax(&s_box[2], px); atomicMax(&s_box[3], py);
+    }
+    __syncthreads();
+    if (t == 0) {
+        int4 b;
+        if (s_box[2] >= 0) {
+            b.x = s_box[0] * 8; b.y = s_box[1] * 8;
+            b.z = min(127, (s_box[2] + 1) * 8); b.w = min(127, (s_box[3] + 1) * 8);
+        } else {
+            b = make_int4(0, 0, 127, 127);
+        }
+        reinterpret_cast<int4*>(bbox_out)[img] = b;
+    }
+}
+
+}  // namespace cnnacc

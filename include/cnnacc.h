@@ -1,0 +1,130 @@
+/*
+ * cnnacc.h -- C ABI of the B200 conv-stack accelerator (libcnnacc.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  Every entry point is extern "C",
+ * takes plain pointers and sizes, returns an int status, and never lets a C++ exception or a
+ * torch type cross.  Each one names the reference interface it replaces (file:line under
+ * /root/reference/).  INTEGRATION.md shows the ctypes stubs a maintainer of the reference adds.
+ *
+ * Status codes (SURVEY.md 8b "Error conventions"):
+ *    0  success
+ *   -1  timeout                       (fast_readout.c:91 start_and_wait -> -1; Python: TimeoutError)
+ *   -2  bad argument / size / state   (pynq_inference.py:189,214 asserts;      Python: ValueError)
+ *   -3  CUDA error                    (pynq_inference.py:128 RuntimeError;     Python: RuntimeError)
+ *   -4  not initialised: no weights / no classifier / no image loaded          (Python: RuntimeError)
+ * There is no CPU fallback: without a CUDA device every call that computes returns -3.
+ *
+ * Threading: one handle = one device + one stream.  A handle is not thread-safe (neither is the
+ * reference: arm_cnn.c:30-32 static scratch); distinct handles are independent.
+ */
+#ifndef CNNACC_H
+#define CNNACC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNNACC_OK            0
+#define CNNACC_ERR_TIMEOUT  (-1)
+#define CNNACC_ERR_ARG      (-2)
+#define CNNACC_ERR_CUDA     (-3)
+#define CNNACC_ERR_STATE    (-4)
+
+#define CNNACC_WEIGHT_BYTES  23184   /* 144 + 4608 + 18432          arm_cnn.c:169-173 */
+#define CNNACC_IMG           128     /* native image side            arm_cnn.c:165     */
+#define CNNACC_FEAT_CH       64      /* final channels               arm_cnn.c:167     */
+#define CNNACC_FEAT_BYTES    16384   /* 64 x 16 x 16                 arm_cnn.c:155     */
+#define CNNACC_BRAM_CHANNELS 112     /* 16 + 32 + 64 feature BRAMs   cnn_acc_top.v:48-54 */
+#define CNNACC_L2_CH_OFFSET  48      /* CH_OFF                       realtime_detect.py:33 */
+
+/* flags for the batch calls */
+#define CNNACC_FLAG_DEVICE_PTRS   0x1u  /* image / feature / result pointers are device memory of the handle's GPU */
+#define CNNACC_FLAG_DIRECT        0x2u  /* use the generic per-layer kernels even for 128x128 (cross-check path) */
+#define CNNACC_FLAG_KEEP_MAPS     0x4u  /* keep image 0's layer-0/1 maps for cnnacc_read_feature_map (BRAM ch 0-47) */
+#define CNNACC_FLAG_CLS_GIVEN     0x8u  /* classify_batch: cls[] is an INPUT (bbox_vec's cls_idx argument), not written */
+
+typedef struct cnnacc_handle cnnacc_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------
+ * Replaces Overlay(bitstream) + IP/DMA discovery (pynq_inference.py:98-155, realtime_detect.py:247-286)
+ * and open_devmem (fast_readout.c:99-113; NULL on failure -> here *out = NULL and a negative code). */
+int cnnacc_create(int device_id, cnnacc_handle **out);
+int cnnacc_destroy(cnnacc_handle *h);
+/* Run later launches on a caller-owned CUDA stream (cudaStream_t as void*); NULL -> the handle's own. */
+int cnnacc_set_stream(cnnacc_handle *h, void *cuda_stream);
+/* Last error text of this handle (or of create when h == NULL).  Never NULL. */
+const char *cnnacc_last_error(const cnnacc_handle *h);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t cnnacc_launch_count(const cnnacc_handle *h);
+
+/* ---- configuration -------------------------------------------------------------------------
+ * load_weights: the one-off DMA of weights.bin into weight BRAM (pynq_inference.py:186-207,
+ * realtime_detect.py:288-296); n must be 23184.  parse_kernels (arm_cnn.c:43-59) runs here once,
+ * not per image (arm_cnn.c:186). */
+int cnnacc_load_weights(cnnacc_handle *h, const uint8_t *weights_bin, size_t n);
+/* set_shifts: AXI reg 10 write, s0 | s1<<5 | s2<<10 (pynq_inference.py:226-229).  The hardware
+ * masks with 0x1F; here values outside 0..31 are rejected with -2 (C >> by >=32 is undefined). */
+int cnnacc_set_shifts(cnnacc_handle *h, int s0, int s1, int s2);
+int cnnacc_get_shifts(const cnnacc_handle *h, int *s3);
+
+/* ---- the hot path: batched conv stack ------------------------------------------------------
+ * Replaces cnn_infer (arm_cnn.c:159-198) / FPGAEngine.run (realtime_detect.py:313-363) for n images.
+ *   imgs  : [n][H][W] u8          feats : [n][64][H/8][W/8] u8   (CHW per image, arm_cnn.c:64-65)
+ * H, W multiples of 16.  128x128 runs the fused sm_100a kernel; other sizes the generic kernels.
+ * Host pointers: the call stages through pinned buffers, overlapping H2D / compute / D2H, and
+ * returns when feats is complete.  Device pointers: asynchronous on the handle's stream. */
+int cnnacc_run_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n, int H, int W,
+                     uint8_t *feats, uint32_t flags);
+
+/* ---- single-image register-style protocol (CNNAccelerator / fast_readout.c) ----------------
+ * load_image   : DMA of one 128x128 image into input BRAM        (pynq_inference.py:209-224)
+ * start        : control reg bit 0                                (pynq_inference.py:231-234)
+ * status       : status reg: bit0 busy, bit1 done, bits3:2 layer (pynq_inference.py:65, :240-246)
+ * wait         : start_and_wait's poll loop, 0 or -1 on timeout  (fast_readout.c:77-92)
+ * read_features: read_features_full, n_ch x 256 bytes from BRAM channel ch_off (fast_readout.c:33-45)
+ * read_feature_map: read_feature_map(channel, n) over the 112-channel map: 0-15 layer 0 (4096 B each),
+ *                16-47 layer 1 (1024 B), 48-111 layer 2 (256 B)   (pynq_inference.py:253-265, cnn_acc_top.v:48-54) */
+int cnnacc_load_image(cnnacc_handle *h, const uint8_t *img, size_t n);
+int cnnacc_start(cnnacc_handle *h);
+int cnnacc_status(cnnacc_handle *h);
+int cnnacc_wait(cnnacc_handle *h, int timeout_us);
+int cnnacc_read_features(cnnacc_handle *h, uint8_t *out, int n_ch, int ch_off);
+int cnnacc_read_feature_map(cnnacc_handle *h, int channel, int num_values, uint8_t *out);
+/* One image in, features out, lowest latency (FPGAEngine.run / ARMEngine.run shape,
+ * realtime_detect.py:313-363,422-436).  Reports device time of the conv stack and of the readback. */
+int cnnacc_infer_one(cnnacc_handle *h, const uint8_t *img, uint8_t *feat, float *conv_ms, float *read_ms);
+
+/* ---- follow-on kernels: spatial-bin pool + linear + softmax + CAM bbox ---------------------
+ * load_classifier: fc_w [n_cls][1024] f32 row-major, fc_b [n_cls] (realtime_detect.py:533-545), n_cls <= 16.
+ * classify_batch : classify_vec + bbox_vec (realtime_detect.py:68-116) on feats [n][64][256] u8.
+ *                  probs [n][n_cls] f32, cls [n] i32, bbox [n][4] i32 (x1,y1,x2,y2); any output may be NULL.
+ * infer_batch    : run_batch (128x128) followed by classify_batch without the features leaving the GPU. */
+int cnnacc_load_classifier(cnnacc_handle *h, const float *fc_w, const float *fc_b, int n_cls);
+int cnnacc_classify_batch(cnnacc_handle *h, const uint8_t *feats, int64_t n,
+                          float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
+int cnnacc_infer_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n,
+                       float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
+
+/* ---- host memory the DMA engines can stream from (pynq.allocate, realtime_detect.py:293,301) */
+int cnnacc_alloc_host(size_t bytes, void **out);
+int cnnacc_free_host(void *p);
+
+/* ---- timing on the handle's stream (CUDA events; bench.py) ---------------------------------- */
+int cnnacc_timer_start(cnnacc_handle *h);
+int cnnacc_timer_stop(cnnacc_handle *h, float *ms);   /* synchronises the stream */
+int cnnacc_synchronize(cnnacc_handle *h);
+
+/* ---- drop-in for the reference symbol ------------------------------------------------------
+ * Same name and signature as arm_cnn.c:159-162, so ARMEngine's ctypes call
+ * (realtime_detect.py:389-391,427-431) works unchanged against libcnnacc.so.  Uses a lazily
+ * created process-global handle on device 0 guarded by a mutex; weights are re-packed only when
+ * the 23184 bytes change.  Returns 0, or a negative code above. */
+int cnn_infer(const uint8_t *input_img, const uint8_t *weights_bin, const int *shifts, uint8_t *output);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNNACC_H */

@@ -1,0 +1,173 @@
+"""Parity of the CUDA conv stack with the oracle, through the C ABI.  Bit-exact (integer path)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import inputs
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fc():
+    import fpga_cnn_b200 as fc_
+    fc_.load()
+    return fc_
+
+
+@pytest.fixture(scope="module")
+def acc(fc, shipped_weights):
+    a = fc.CNNAccelerator(device=0)
+    a.load_weights(shipped_weights)
+    yield a
+    a.close()
+
+
+@pytest.fixture(scope="module")
+def port():
+    return oracle.load_port()
+
+
+@pytest.mark.parametrize("direct", [False, True], ids=["fused", "direct"])
+@pytest.mark.parametrize("case", inputs.CONV_CASES, ids=lambda c: c["name"])
+def test_golden_cases(case, direct, acc, shipped_weights, conv_golden):
+    wt = inputs.make_weights(case["weights"], shipped_weights)
+    acc.load_weights(wt)
+    acc.set_shifts(*case["shifts"])
+    imgs = inputs.make_images(case["images"], case["n"])
+    got = acc.run_batch(imgs, direct=direct)
+    assert got.shape == (case["n"], 64, 16, 16)
+    assert np.array_equal(got.reshape(case["n"], 64, 256), conv_golden[case["name"]])
+
+
+@pytest.mark.parametrize("case", [c for c in inputs.CONV_CASES if c.get("dump")], ids=lambda c: c["name"])
+def test_intermediate_maps_via_register_protocol(case, acc, shipped_weights, conv_golden):
+    """load_image / start / wait / read_feature_map over BRAM channels 0-111 (pynq_inference.py:209-286)."""
+    acc.load_weights(inputs.make_weights(case["weights"], shipped_weights))
+    acc.set_shifts(*case["shifts"])
+    img = inputs.make_images(case["images"], 1)[0]
+    acc.load_image(img)
+    acc.start_inference()
+    assert acc.wait_done(10.0) >= 0
+    assert (acc.read_reg(0x04) >> 1) & 1
+    l0, l1 = conv_golden[case["name"] + "__l0"], conv_golden[case["name"] + "__l1"]
+    for ch in (0, 7, 15):
+        assert np.array_equal(acc.read_feature_map(ch, 4096), l0[ch].reshape(-1))
+    for ch in (16, 33, 47):
+        assert np.array_equal(acc.read_feature_map(ch, 1024), l1[ch - 16].reshape(-1))
+    assert np.array_equal(acc.read_layer2_output(), conv_golden[case["name"]][0])
+    # dump_fpga_features-style register pokes (write 0x20 / 0x24, read 0x28)
+    acc.write_reg(0x20, 48 + 5); acc.write_reg(0x24, 100)
+    assert acc.read_reg(0x28) == conv_golden[case["name"]][0][5, 100]
+
+
+@pytest.mark.parametrize("direct", [False, True], ids=["fused", "direct"])
+def test_random_batch_vs_oracle(direct, acc, port, shipped_weights):
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        wt = shipped_weights if trial % 2 == 0 else inputs.make_weights(("rng", 300 + trial))
+        sh = (7, 10, 11) if trial % 2 == 0 else (9, 12, 13)
+        n = int(rng.integers(1, 70))
+        imgs = inputs.make_images(("rng", 400 + trial), n)
+        acc.load_weights(wt)
+        acc.set_shifts(*sh)
+        got = acc.run_batch(imgs, direct=direct).reshape(n, 64, 256)
+        want = oracle.port_infer_batch(port, imgs, wt, sh)
+        assert np.array_equal(got, want), f"trial {trial}: {np.argwhere(got != want)[:5]}"
+
+
+@pytest.mark.parametrize("case", inputs.HW_CASES, ids=lambda c: c["name"])
+def test_generic_sizes(case, acc, shipped_weights, conv_golden):
+    acc.load_weights(inputs.make_weights(case["weights"], shipped_weights))
+    acc.set_shifts(*case["shifts"])
+    img = inputs.make_images(case["images"], 1, case["H"], case["W"])
+    got = acc.run_batch(img)
+    assert np.array_equal(got.reshape(64, -1), conv_golden[case["name"]])
+
+
+def test_fused_equals_direct_at_scale(acc, shipped_weights):
+    """Full-size property check: the fused kernel and the per-layer kernels agree on 4096 images (config 2)."""
+    acc.load_weights(shipped_weights)
+    acc.set_shifts(7, 10, 11)
+    imgs = inputs.make_images(("rng", 77), 4096)
+    a = acc.run_batch(imgs)
+    b = acc.run_batch(imgs, direct=True)
+    assert np.array_equal(a, b)
+
+
+def test_ten_thousand_images_vs_oracle(acc, port, shipped_weights):
+    """The north_star gate: 10 000 synthetic images, 100 % byte-equal vs the oracle (multi-process on the host)."""
+    import multiprocessing as mp
+    n = 10000
+    acc.load_weights(shipped_weights)
+    got = {}
+    imgs = inputs.make_images(("rng", 1234), n)
+    for sh in ((2, 4, 6), (7, 10, 11)):
+        acc.set_shifts(*sh)
+        got[sh] = acc.run_batch(imgs).reshape(n, 64, 256)
+    workers = min(mp.cpu_count(), 32)
+    bounds = np.linspace(0, n, workers + 1).astype(int)
+    for sh in got:
+        jobs = [(imgs[bounds[i]:bounds[i + 1]], shipped_weights, sh) for i in range(workers)]
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_oracle_chunk, jobs)
+        want = np.concatenate(parts)
+        bad = np.flatnonzero((got[sh] != want).reshape(n, -1).any(axis=1))
+        assert bad.size == 0, f"shifts {sh}: {bad.size} images differ, first {bad[:5]}"
+
+
+def _oracle_chunk(job):
+    imgs, wt, sh = job
+    return oracle.port_infer_batch(oracle.load_port(), imgs, wt, sh)
+
+
+def test_drop_in_cnn_infer_symbol(fc, shipped_weights, conv_golden):
+    """The reference's ARMEngine.run body against libcnnacc.so (realtime_detect.py:422-436)."""
+    eng = fc.ARMEngine(shipped_weights, shifts=(7, 10, 11))
+    imgs = inputs.make_images(("rng", 1), 3)
+    for i in range(3):
+        feat, conv_ms, read_ms = eng.run(imgs[i])
+        assert feat.shape == (64, 256) and feat.dtype == np.uint8 and read_ms == 0.0
+        assert np.array_equal(feat, conv_golden["rng_shipped_mid"][i])
+
+
+def test_engine_run_surface(fc, shipped_weights, conv_golden):
+    eng = fc.B200Engine(shipped_weights, shifts=(2, 4, 6))
+    imgs = inputs.make_images(("rng", 0), 2)
+    for i in range(2):
+        feat, conv_ms, read_ms = eng.run(imgs[i].reshape(128, 128))
+        assert np.array_equal(feat, conv_golden["rng_shipped_default"][i]) and conv_ms > 0 and read_ms > 0
+
+
+def test_error_conventions(fc, shipped_weights):
+    a = fc.CNNAccelerator()
+    with pytest.raises(RuntimeError):
+        a.run_batch(np.zeros((1, 128, 128), np.uint8))          # weights not loaded
+    with pytest.raises(AssertionError):
+        a.load_weights(np.zeros(100, np.uint8))                 # pynq_inference.py:189
+    a.load_weights(shipped_weights)
+    with pytest.raises(AssertionError):
+        a.load_image(np.zeros(100, np.uint8))                   # pynq_inference.py:214
+    with pytest.raises(ValueError):
+        a.set_shifts(2, 4, 32)
+    with pytest.raises(ValueError):
+        a.run_batch(np.zeros((1, 100, 128), np.uint8))
+    with pytest.raises(RuntimeError):
+        a.start_inference()                                      # no image loaded
+    assert a.run_batch(np.zeros((0, 128, 128), np.uint8)).shape == (0, 64, 16, 16)   # empty batch
+    a.close()
+
+
+def test_device_pointer_path_with_torch(fc, shipped_weights, conv_golden):
+    import torch
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    a.use_stream(torch.cuda.current_stream().cuda_stream)
+    imgs = torch.from_numpy(inputs.make_images(("rng", 1), 8)).cuda()
+    out = a.run_batch(imgs)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(8, 64, 256), conv_golden["rng_shipped_mid"])
+    a.close()
