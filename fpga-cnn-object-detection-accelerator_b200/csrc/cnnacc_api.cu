@@ -157,6 +157,15 @@ int slot_reserve(cnnacc_handle* h, Slot& s, size_t in_bytes, size_t out_bytes, s
     return 0;
 }
 
+// A fused launch whose internal waits timed out reports it through a device status word.
+int check_fused_status(cnnacc_handle* h) {
+    int bits = 0;
+    int e = fused_poll_status(h->fused, &bits);
+    if (e) return fail(h, CNNACC_ERR_CUDA, std::string("status readback: ") + cudaGetErrorString((cudaError_t)e));
+    if (bits) return fail(h, CNNACC_ERR_CUDA, "fused kernel pipeline timeout, status bits " + std::to_string(bits));
+    return 0;
+}
+
 int check_ready(cnnacc_handle* h) {
     if (!h) return CNNACC_ERR_ARG;
     if (!h->weights_loaded) return fail(h, CNNACC_ERR_STATE, "weights not loaded (call cnnacc_load_weights)");
@@ -305,7 +314,7 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
         CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, s.stream));
     }
     for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
-    return CNNACC_OK;
+    return check_fused_status(h);
 }
 
 int cnnacc_load_image(cnnacc_handle* h, const uint8_t* img, size_t n) {
@@ -365,6 +374,7 @@ int cnnacc_read_feature_map(cnnacc_handle* h, int channel, int num_values, uint8
     else if (channel < 48) { off = 16 * 4096 + (size_t)(channel - 16) * 1024;    depth = 1024; }
     else                   { off = 16 * 4096 + 32 * 1024 + (size_t)(channel - 48) * 256; depth = 256; }
     if (num_values < 0 || (size_t)num_values > depth) return fail(h, CNNACC_ERR_ARG, "num_values exceeds the channel's BRAM depth");
+    { int rc = check_fused_status(h); if (rc) return rc; }
     std::memcpy(out, h->h_bram + off, (size_t)num_values);
     return CNNACC_OK;
 }
@@ -399,7 +409,7 @@ int cnnacc_infer_one(cnnacc_handle* h, const uint8_t* img, uint8_t* feat, float*
     std::memcpy(feat, h_l2, CNNACC_FEAT_BYTES);
     if (conv_ms) CU(h, cudaEventElapsedTime(conv_ms, h->ev_a, h->ev_b));
     if (read_ms) CU(h, cudaEventElapsedTime(read_ms, h->ev_b, h->ev_c));
-    return CNNACC_OK;
+    return check_fused_status(h);
 }
 
 int cnnacc_load_classifier(cnnacc_handle* h, const float* fc_w, const float* fc_b, int n_cls) {
@@ -511,7 +521,7 @@ int cnnacc_timer_stop(cnnacc_handle* h, float* ms) {
     CU(h, cudaEventRecord(h->ev_t1, h->stream));
     CU(h, cudaEventSynchronize(h->ev_t1));
     CU(h, cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
-    return CNNACC_OK;
+    return check_fused_status(h);
 }
 
 int cnnacc_synchronize(cnnacc_handle* h) {
@@ -519,7 +529,7 @@ int cnnacc_synchronize(cnnacc_handle* h) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
-    return CNNACC_OK;
+    return check_fused_status(h);
 }
 
 // ---- drop-in for arm_cnn.c:159-162 -------------------------------------------------------------
