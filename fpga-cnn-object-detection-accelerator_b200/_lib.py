@@ -4,7 +4,8 @@ import os
 import subprocess
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libcnnacc.so")
+# CNNACC_LIB_PATH: tuning experiments load an alternative build of the same library (tools/build_variants.sh)
+LIB_PATH = os.environ.get("CNNACC_LIB_PATH") or os.path.join(_DIR, "libcnnacc.so")
 CSRC = os.path.join(_DIR, "csrc")
 
 OK, ERR_TIMEOUT, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
@@ -22,6 +23,7 @@ SYMBOLS = {
     "cnnacc_load_weights": (_c.c_int, [_H, _c.c_void_p, _c.c_size_t]),
     "cnnacc_set_shifts": (_c.c_int, [_H, _c.c_int, _c.c_int, _c.c_int]),
     "cnnacc_get_shifts": (_c.c_int, [_H, _c.POINTER(_c.c_int)]),
+    "cnnacc_pack_weights_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "cnnacc_run_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
     "cnnacc_load_image": (_c.c_int, [_H, _c.c_void_p, _c.c_size_t]),
     "cnnacc_start": (_c.c_int, [_H]),
