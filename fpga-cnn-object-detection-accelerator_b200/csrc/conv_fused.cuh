@@ -244,51 +244,65 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 
     if (warp < kL0Warps) {
         // =============== layer 0: dp4a on CUDA cores =============================================================
-        // One warp-iteration = half a pooled row: 32 pooling windows x 16 out-channels.  Lanes 0-15 take the even
-        // windows and 16-31 the odd ones so the 16-byte act1 stores of a quarter-warp are contiguous.
+        // One warp-iteration = one pooled row: 64 pooling windows x 16 out-channels, two adjacent windows per lane so
+        // the weight words (uniform registers) and the input words are fetched once for 384 dp4a.
         for (int k = 0; k < n_local; k++) {
             const int img = (int)blockIdx.x + k * (int)gridDim.x;
             const int slot = k & 1;
             wait_or_flag(bar(kBarInFull0 + slot), (uint32_t)(k >> 1) & 1, kErrInputTimeout);
             const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + (slot ? kOffIn1 : kOffIn0));
 #pragma unroll 1
-            for (int u = warp; u < 128; u += kL0Warps) {         // unit = half a pooled row
+            for (int yp = warp; yp < 64; yp += kL0Warps) {
                 // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
-                // ones.  Units 0-55 write rows 1-28 (top tiles only); units >= 56 write rows >= 29 (row 32 on: bottom tiles).
-                if (k > 0 && u == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                if (k > 0 && u >= 56 && u - kL0Warps < 56) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                const int yp = u >> 1;
-                const int xp = (u & 1) * 32 + 2 * (lane & 15) + (lane >> 4);
-                const int cb = 2 * xp + 15;                                      // slot byte of pixel column 2xp-1
-                const uint32_t* rp = in_w + (2 * yp) * (kInPitch / 4) + (cb >> 2);
-                const int sh = (cb & 3) * 8;
-                uint32_t A[4];
+                // ones.  This unit writes row yp+1.
+                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                // windows xp = 2*lane and 2*lane+1 need pixel columns 4*lane-1 .. 4*lane+4 = slot bytes 4*lane+15 .. 4*lane+20
+                const uint32_t* rp = in_w + (2 * yp) * (kInPitch / 4) + lane + 3;
+                uint32_t A[4], B[4];
 #pragma unroll
-                for (int r = 0; r < 4; r++) A[r] = __funnelshift_r(rp[r * (kInPitch / 4)], rp[r * (kInPitch / 4) + 1], sh);
-                int pooled[16];
-#pragma unroll
-                for (int o = 0; o < 16; o++) {
-                    const uint32_t l0 = P.w0[o][0], l1 = P.w0[o][1], l2 = P.w0[o][2];
-                    const uint32_t h0 = P.w0[o][3], h1 = P.w0[o][4], h2 = P.w0[o][5];
-                    int a00 = dp4a_u8s8(A[0], l0, dp4a_u8s8(A[1], l1, dp4a_u8s8(A[2], l2, 0)));
-                    int a01 = dp4a_u8s8(A[0], h0, dp4a_u8s8(A[1], h1, dp4a_u8s8(A[2], h2, 0)));
-                    int a10 = dp4a_u8s8(A[1], l0, dp4a_u8s8(A[2], l1, dp4a_u8s8(A[3], l2, 0)));
-                    int a11 = dp4a_u8s8(A[1], h0, dp4a_u8s8(A[2], h1, dp4a_u8s8(A[3], h2, 0)));
-                    pooled[o] = max4(a00, a01, a10, a11);
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t w0 = rp[r * (kInPitch / 4)], w1 = rp[r * (kInPitch / 4) + 1], w2 = rp[r * (kInPitch / 4) + 2];
+                    A[r] = __funnelshift_r(w0, w1, 24);
+                    B[r] = __funnelshift_r(w1, w2, 8);
                 }
-                uint4 v;
-                v.x = act_pack4(pooled[0], pooled[1], pooled[2], pooled[3], P.shift0);
-                v.y = act_pack4(pooled[4], pooled[5], pooled[6], pooled[7], P.shift0);
-                v.z = act_pack4(pooled[8], pooled[9], pooled[10], pooled[11], P.shift0);
-                v.w = act_pack4(pooled[12], pooled[13], pooled[14], pooled[15], P.shift0);
-                *reinterpret_cast<uint4*>(smem + kOffA1 + (yp + 1) * kA1P + ((xp + 1) & 1) * kA1Q + ((xp + 1) >> 1) * 16) = v;
+                uint32_t va[4], vb[4];
+#pragma unroll
+                for (int o4 = 0; o4 < 4; o4++) {
+                    int pa[4], pb[4];
+#pragma unroll
+                    for (int oo = 0; oo < 4; oo++) {
+                        const int o = o4 * 4 + oo;
+                        const uint32_t l0 = P.w0[o][0], l1 = P.w0[o][1], l2 = P.w0[o][2];
+                        const uint32_t h0 = P.w0[o][3], h1 = P.w0[o][4], h2 = P.w0[o][5];
+                        int a00 = dp4a_u8s8(A[0], l0, dp4a_u8s8(A[1], l1, dp4a_u8s8(A[2], l2, 0)));
+                        int a01 = dp4a_u8s8(A[0], h0, dp4a_u8s8(A[1], h1, dp4a_u8s8(A[2], h2, 0)));
+                        int a10 = dp4a_u8s8(A[1], l0, dp4a_u8s8(A[2], l1, dp4a_u8s8(A[3], l2, 0)));
+                        int a11 = dp4a_u8s8(A[1], h0, dp4a_u8s8(A[2], h1, dp4a_u8s8(A[3], h2, 0)));
+                        int b00 = dp4a_u8s8(B[0], l0, dp4a_u8s8(B[1], l1, dp4a_u8s8(B[2], l2, 0)));
+                        int b01 = dp4a_u8s8(B[0], h0, dp4a_u8s8(B[1], h1, dp4a_u8s8(B[2], h2, 0)));
+                        int b10 = dp4a_u8s8(B[1], l0, dp4a_u8s8(B[2], l1, dp4a_u8s8(B[3], l2, 0)));
+                        int b11 = dp4a_u8s8(B[1], h0, dp4a_u8s8(B[2], h1, dp4a_u8s8(B[3], h2, 0)));
+                        pa[oo] = max4(a00, a01, a10, a11);
+                        pb[oo] = max4(b00, b01, b10, b11);
+                    }
+                    va[o4] = act_pack4(pa[0], pa[1], pa[2], pa[3], P.shift0);
+                    vb[o4] = act_pack4(pb[0], pb[1], pb[2], pb[3], P.shift0);
+                }
+                // window 2*lane -> halo column 2*lane+1 (odd plane, index lane); window 2*lane+1 -> column 2*lane+2 (even
+                // plane, index lane+1): both 16-byte stores are contiguous across the warp
+                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P;
+                *reinterpret_cast<uint4*>(row + kA1Q + lane * 16) = make_uint4(va[0], va[1], va[2], va[3]);
+                *reinterpret_cast<uint4*>(row + (lane + 1) * 16) = make_uint4(vb[0], vb[1], vb[2], vb[3]);
                 if (P.dump_l0) {                         // debug / register-protocol path: BRAM channels 0-15
-                    uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + xp;
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
 #pragma unroll
-                    for (int c = 0; c < 16; c++) d[c * 4096] = (uint8_t)(w[c >> 2] >> (8 * (c & 3)));
+                    for (int c = 0; c < 16; c++) {
+                        d[c * 4096] = (uint8_t)(va[c >> 2] >> (8 * (c & 3)));
+                        d[c * 4096 + 1] = (uint8_t)(vb[c >> 2] >> (8 * (c & 3)));
+                    }
                 }
-                if (u <= 65 && u + kL0Warps > 65) {      // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
+                if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
                     fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(kBarA1TopReady));
