@@ -70,6 +70,9 @@ constexpr int kOffStage = kOffB2 + kB2Bytes;          // 199680
 constexpr int kOffBar   = kOffStage + kStageBytes;    // 216064
 constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
 
+#ifndef CNNACC_L0_DP4A
+#define CNNACC_L0_DP4A 0      // 1 = layer 0 on the dp4a pipe (the first design; kept for the ablation in profiles/)
+#endif
 #ifndef CNNACC_L0_WARPS
 #define CNNACC_L0_WARPS 16
 #endif
@@ -77,7 +80,7 @@ constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
 #define CNNACC_EPI_WARPS 4
 #endif
 constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
-static_assert(kL0Warps % 4 == 0 && kL0Warps <= 16 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
+static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
 constexpr int kWarpMma = kL0Warps + kEpiWarps, kWarpTma = kWarpMma + 1;
 constexpr int kFusedThreads = (kWarpTma + 1) * 32;    // 576
 constexpr uint32_t kTmemCols = 512;
@@ -98,7 +101,8 @@ constexpr int kErrInputTimeout = 1, kErrMmaTimeout = 2, kErrEmptyTimeout = 4, kE
               kErrAct1Timeout = 16, kErrAct2Timeout = 32, kErrSlotTimeout = 64;
 
 struct FusedParams {
-    uint32_t w0[16][6];          // layer-0 dp4a words per out-channel: lo[dy], hi[dy]  (constant bank)
+    uint32_t w0[16][6];          // layer-0 dp4a words per out-channel: lo[dy], hi[dy]  (constant bank; CNNACC_L0_DP4A build)
+    uint32_t w0f[8][32];         // layer-0 mma.sync B fragments: [block = py*4 + ol][lane]
     int shift0, shift1, shift2;
     int n_images;
     const uint8_t* b1;           // packed layer-1 B operand (kB1Bytes)
@@ -190,6 +194,14 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory"); }
 
+// Warp-level int8 MMA for layer 0 (K = 9 is too thin for a 128-row tcgen05 tile without a re-layout pass):
+// D(16x8,s32) += A(16x16,u8) * B(16x8,s8).  Fragments (lane = 4*g + t): a0/a1 = rows g / g+8, k = 4t..4t+3;
+// b0 = k 4t..4t+3 of column g; c0,c1 = row g cols 2t,2t+1; c2,c3 = row g+8.  SASS: IMMA.16816.U8.S8.
+__device__ __forceinline__ void imma_16816(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
 // arm_cnn.c:127-135 for one accumulator: shift, then saturate to [0,255] (negatives stay negative under >>).
 __device__ __forceinline__ uint32_t act_u8(int v, int shift) {
     uint32_t d;
@@ -243,6 +255,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     };
 
     if (warp < kL0Warps) {
+#if CNNACC_L0_DP4A
         // =============== layer 0: dp4a on CUDA cores =============================================================
         // One warp-iteration = one pooled row: 64 pooling windows x 16 out-channels, two adjacent windows per lane so
         // the weight words (uniform registers) and the input words are fetched once for 384 dp4a.
@@ -312,6 +325,73 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
         }
+#else
+        // =============== layer 0: warp-level int8 MMA (mma.sync m16n8k16), accumulators in registers ===============
+        // A row = one 2x2 pooling window, K = its 4x4 input patch (k = 4*patch row + patch column), N = 8 columns =
+        // (4 out-channels) x (horizontal window member px); 8 column blocks = (vertical member py) x (oc%4).  Lane
+        // (g,t) ends up with all four members of window g (and g+8) for out-channels 4t..4t+3: the pool is
+        // thread-local and the result is one packed word of the 16-channel act1 vector.  One warp-iteration = one
+        // pooled row = 4 fragments of 16 windows (even windows in rows 0-7, odd ones in rows 8-15 so that both
+        // 128-byte stores of a fragment are contiguous in their parity plane).
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t bfr[8];
+#pragma unroll
+        for (int blk = 0; blk < 8; blk++) bfr[blk] = P.w0f[blk][lane];
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            const int slot = k & 1;
+            wait_or_flag(bar(kBarInFull0 + slot), (uint32_t)(k >> 1) & 1, kErrInputTimeout);
+            const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + (slot ? kOffIn1 : kOffIn0));
+#pragma unroll 1
+            for (int yp = warp; yp < 64; yp += kL0Warps) {
+                // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
+                // ones.  This unit writes row yp+1.
+                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                // patch row t of windows 2g+16f (a0) and 2g+16f+1 (a1): image row 2yp-1+t, columns 4g+32f-1 .. +4
+                const uint32_t* rp = in_w + (2 * yp + t) * (kInPitch / 4) + g + 3;
+                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P + g * 16 + t * 4;
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                    const uint32_t w0 = rp[8 * f], w1 = rp[8 * f + 1], w2 = rp[8 * f + 2];
+                    const uint32_t a0 = __funnelshift_r(w0, w1, 24), a1 = __funnelshift_r(w1, w2, 8);
+                    int c[8][4];
+#pragma unroll
+                    for (int blk = 0; blk < 8; blk++) {
+                        c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0;
+                        imma_16816(c[blk], a0, a1, bfr[blk]);
+                    }
+                    int pe[4], po[4];
+#pragma unroll
+                    for (int ol = 0; ol < 4; ol++) {
+                        pe[ol] = max4(c[ol][0], c[ol][1], c[4 + ol][0], c[4 + ol][1]);
+                        po[ol] = max4(c[ol][2], c[ol][3], c[4 + ol][2], c[4 + ol][3]);
+                    }
+                    const uint32_t we = act_pack4(pe[0], pe[1], pe[2], pe[3], P.shift0);
+                    const uint32_t wo = act_pack4(po[0], po[1], po[2], po[3], P.shift0);
+                    // window 2g+16f -> halo column odd (plane 1, index g+8f); window +1 -> even plane, index g+8f+1
+                    *reinterpret_cast<uint32_t*>(row + kA1Q + f * 128) = we;
+                    *reinterpret_cast<uint32_t*>(row + 16 + f * 128) = wo;
+                    if (P.dump_l0) {                     // debug / register-protocol path: BRAM channels 0-15
+                        uint8_t* d = P.dump_l0 + (size_t)img * 65536 + (size_t)(4 * t) * 4096 + yp * 64 + 2 * g + 16 * f;
+#pragma unroll
+                        for (int ol = 0; ol < 4; ol++) {
+                            d[ol * 4096] = (uint8_t)(we >> (8 * ol));
+                            d[ol * 4096 + 1] = (uint8_t)(wo >> (8 * ol));
+                        }
+                    }
+                }
+                if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
+                    fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarA1TopReady));
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
+        }
+#endif
     } else if (warp < kWarpMma) {
         // =============== epilogue warps ==========================================================================
         const int e = warp - kL0Warps;
@@ -504,6 +584,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 struct FusedWeights {
     bool ready = false;
     uint32_t w0[16][6];
+    uint32_t w0f[8][32];
     uint8_t* d_b1 = nullptr;
     uint8_t* d_b2 = nullptr;
     int* d_status = nullptr;
@@ -527,7 +608,19 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // Pure host permutation of weights.bin (parse_kernels, arm_cnn.c:43-59, done once) into the three operand layouts.
-inline void fused_pack_weights(const uint8_t* wbin, uint32_t w0[16][6], uint8_t* b1, uint8_t* b2) {
+inline void fused_pack_weights(const uint8_t* wbin, uint32_t w0[16][6], uint32_t w0f[8][32], uint8_t* b1, uint8_t* b2) {
+    // layer 0, mma.sync B fragments: lane (g,t) of block (py, ol) holds patch row r = t, columns c = 0..3 of
+    // output column n = g -> out-channel 4*(g>>1) + ol, horizontal member px = g&1:  w0[oc][r - py][c - px]
+    for (int blk = 0; blk < 8; blk++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int py = blk >> 2, ol = blk & 3, g = lane >> 2, t = lane & 3, oc = 4 * (g >> 1) + ol, px = g & 1;
+            uint32_t word = 0;
+            for (int c = 0; c < 4; c++) {
+                const int dy = t - py, dx = c - px;
+                if (dy >= 0 && dy <= 2 && dx >= 0 && dx <= 2) word |= (uint32_t)weight_byte(wbin, 0, oc, 0, dy * 3 + dx) << (8 * c);
+            }
+            w0f[blk][lane] = word;
+        }
     std::memset(b1, 0, kB1Bytes);
     std::memset(b2, 0, kB2Bytes);
     for (int o = 0; o < 16; o++)
@@ -560,7 +653,7 @@ inline void fused_pack_weights(const uint8_t* wbin, uint32_t w0[16][6], uint8_t*
 inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
     fw.ready = false;
     std::vector<uint8_t> b1(kB1Bytes), b2(kB2Bytes);
-    fused_pack_weights(wbin, fw.w0, b1.data(), b2.data());
+    fused_pack_weights(wbin, fw.w0, fw.w0f, b1.data(), b2.data());
     cudaError_t e;
     if (!fw.d_b1 && (e = cudaMalloc(&fw.d_b1, kB1Bytes)) != cudaSuccess) return (int)e;
     if (!fw.d_b2 && (e = cudaMalloc(&fw.d_b2, kB2Bytes)) != cudaSuccess) return (int)e;
@@ -600,6 +693,7 @@ inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8
     if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
     FusedParams P;
     std::memcpy(P.w0, fw.w0, sizeof(P.w0));
+    std::memcpy(P.w0f, fw.w0f, sizeof(P.w0f));
     P.shift0 = shifts[0]; P.shift1 = shifts[1]; P.shift2 = shifts[2];
     P.n_images = (int)n;
     P.b1 = fw.d_b1; P.b2 = fw.d_b2;

@@ -28,12 +28,12 @@ B1_SLAB = 4096
 
 def pack(weights):
     lib = fc.load()
-    w0 = np.zeros(96, np.uint32)
+    w0 = np.zeros(352, np.uint32)
     b1 = np.zeros(32768, np.uint8)
     b2 = np.zeros(18432, np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     assert lib.cnnacc_pack_weights_host(p(weights), weights.size, p(w0), p(b1), p(b2)) == 0
-    return w0.reshape(16, 6), b1, b2
+    return w0[:96].reshape(16, 6), w0[96:].reshape(8, 32), b1, b2
 
 
 def operand(buf, start, lbo, sbo, rows, signed):
@@ -66,6 +66,25 @@ def layer0_dp4a(img, w0, shift):
         a10 = sum((A[d + 1] * w[o, d]).sum(-1) for d in range(3))
         a11 = sum((A[d + 1] * w[o, 3 + d]).sum(-1) for d in range(3))
         out[o] = act(np.maximum(np.maximum(a00, a01), np.maximum(a10, a11)), shift)
+    return out
+
+
+def layer0_imma(img, w0f, shift):
+    """Layer 0 as the mma.sync fragments compute it: A row = a window's 4x4 patch (k = 4*row + col), B fragment word
+    of lane 4*n + r in block (py, ol) = patch row r of output column n -> (oc = 4*(n>>1) + ol, px = n&1)."""
+    pad = np.zeros((130, 160), np.int64)
+    pad[1:129, 16:144] = img
+    yp, xp = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    patch = np.stack([np.stack([pad[2 * yp + r, 2 * xp + 15 + c] for c in range(4)], -1) for r in range(4)], -2)   # [64][64][r][c]
+    B = np.zeros((8, 8, 4, 4), np.int64)                                  # [blk][n][r][c]
+    for c in range(4):
+        B[:, :, :, c] = ((w0f >> (8 * c)) & 0xFF).astype(np.uint8).view(np.int8).reshape(8, 8, 4)
+    D = np.einsum("yxrc,bnrc->yxbn", patch, B)                            # [64][64][blk][n]
+    out = np.zeros((16, 64, 64), np.uint8)
+    for n2 in range(4):
+        for ol in range(4):
+            members = [D[:, :, py * 4 + ol, 2 * n2 + px] for py in range(2) for px in range(2)]
+            out[4 * n2 + ol] = act(np.maximum.reduce(members), shift)
     return out
 
 
@@ -140,9 +159,10 @@ def test_packed_operands_reproduce_the_oracle(wkind, shifts):
     wt = inputs.make_weights(wkind, shipped)
     img = inputs.make_images(("rng", 42), 1)[0]
     want, want_l0, want_l1 = np_oracle.infer(img, np_oracle.unpack_weights(wt), shifts, return_all=True)
-    w0, b1, b2 = pack(wt)
+    w0, w0f, b1, b2 = pack(wt)
     l0 = layer0_dp4a(img, w0, shifts[0])
     assert np.array_equal(l0, want_l0), "layer-0 dp4a words"
+    assert np.array_equal(layer0_imma(img, w0f, shifts[0]), want_l0), "layer-0 mma.sync B fragments"
     l1 = layer1_umma(store_act1(l0), b1, shifts[1])
     assert np.array_equal(l1, want_l1), "layer-1 Toeplitz operand / descriptors"
     l2 = layer2_umma(store_act2(l1), b2, shifts[2])
@@ -152,5 +172,5 @@ def test_packed_operands_reproduce_the_oracle(wkind, shifts):
 def test_toeplitz_density():
     """56.25 % of the layer-1 B operand is structurally non-zero (36 of 64 (member, patch pixel) pairs)."""
     wt = np.full(23184, 1, np.uint8)
-    _, b1, _ = pack(wt)
+    _, _, b1, _ = pack(wt)
     assert np.count_nonzero(b1) == 36 * 32 * 16
