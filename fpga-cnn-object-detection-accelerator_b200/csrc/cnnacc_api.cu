@@ -49,7 +49,10 @@ struct cnnacc_handle {
     size_t cap_l0 = 0, cap_l1 = 0, cap_feat = 0;
     Slot slots[kSlots];
     // single-image protocol state
-    uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned
+    uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned + mapped: the batch-1 path runs zero-copy on them
+    uint8_t *h_img_dev = nullptr, *h_bram_dev = nullptr;   // their device addresses
+    CUtensorMap one_map;                            // tensor map over h_img (1 image), encoded once
+    bool one_map_ok = false;
     uint8_t *d_img1 = nullptr, *d_bram = nullptr;
     bool image_loaded = false, started = false;
     int64_t launches = 0;
@@ -209,8 +212,10 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (auto& s : h->slots)
         if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaHostAlloc(&h->h_img, CNNACC_IMG * CNNACC_IMG, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-    if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&h->h_img, CNNACC_IMG * CNNACC_IMG, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer(&h->h_img_dev, h->h_img, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if ((e = cudaHostGetDevicePointer(&h->h_bram_dev, h->h_bram, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaMalloc(&h->d_img1, CNNACC_IMG * CNNACC_IMG)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_bram, kBramBytes)) != cudaSuccess) return bail("cudaMalloc", e);
     *out = h;
@@ -402,14 +407,33 @@ int cnnacc_infer_one(cnnacc_handle* h, const uint8_t* img, uint8_t* feat, float*
     if (!img || !feat) return fail(h, CNNACC_ERR_ARG, "NULL argument");
     CU(h, cudaSetDevice(h->device));
     if (h->started) CU(h, cudaEventSynchronize(h->ev_done));
-    const bool maps = needs_maps(h, CNNACC_IMG, CNNACC_IMG, 0);
-    uint8_t *l0 = h->d_bram, *l1 = h->d_bram + 16 * 4096, *l2 = l1 + 32 * 1024;
+    uint8_t* h_l2 = h->h_bram + 16 * 4096 + 32 * 1024;
+    const auto t0 = std::chrono::steady_clock::now();
     std::memcpy(h->h_img, img, CNNACC_FEAT_BYTES);
+    if (h->fused.ready) {
+        // Zero-copy: the kernel TMA-loads the image straight from mapped pinned host memory and its 16 KiB bulk
+        // store lands in mapped pinned host memory -- one launch, one stream sync, no copy-engine round trips.
+        if (!h->one_map_ok) {
+            if (fused_encode_map(h->h_img_dev, 1, &h->one_map)) return fail(h, CNNACC_ERR_CUDA, "tensor map over the pinned image buffer");
+            h->one_map_ok = true;
+        }
+        uint8_t* l2_dev = h->h_bram_dev + 16 * 4096 + 32 * 1024;
+        rc = launch_fused_map(h->fused, h->stream, h->one_map, 1, l2_dev, h->shifts, h->sm_count, nullptr, nullptr);
+        h->launches++;
+        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+        CU(h, cudaStreamSynchronize(h->stream));
+        const auto t1 = std::chrono::steady_clock::now();
+        std::memcpy(feat, h_l2, CNNACC_FEAT_BYTES);
+        if (conv_ms) *conv_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+        if (read_ms) *read_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        return check_fused_status(h);
+    }
+    // generic path (no fused kernel): staged copies around the per-layer kernels
+    uint8_t *l0 = h->d_bram, *l1 = h->d_bram + 16 * 4096, *l2 = l1 + 32 * 1024;
     CU(h, cudaMemcpyAsync(h->d_img1, h->h_img, CNNACC_IMG * CNNACC_IMG, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaEventRecord(h->ev_a, h->stream));
-    if ((rc = conv_stack_device(h, h->stream, h->d_img1, 1, CNNACC_IMG, CNNACC_IMG, l2, 0, maps ? l0 : nullptr, maps ? l1 : nullptr))) return rc;
+    if ((rc = conv_stack_device(h, h->stream, h->d_img1, 1, CNNACC_IMG, CNNACC_IMG, l2, 0, l0, l1))) return rc;
     CU(h, cudaEventRecord(h->ev_b, h->stream));
-    uint8_t* h_l2 = h->h_bram + 16 * 4096 + 32 * 1024;
     CU(h, cudaMemcpyAsync(h_l2, l2, CNNACC_FEAT_BYTES, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaEventRecord(h->ev_c, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

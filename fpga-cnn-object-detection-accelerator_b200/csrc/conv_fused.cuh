@@ -111,6 +111,7 @@ struct FusedParams {
     uint8_t* dump_l0;            // optional [n][16][64][64]
     uint8_t* dump_l1;            // optional [n][32][32][32]
     int* status;                 // device int, OR-ed error bits
+    int* status_host;            // the same in mapped pinned host memory: polled without a CUDA call
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -576,7 +577,11 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     // ---- teardown ---------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (tid == 0 && *s_err) atomicOr(P.status, *s_err);
+    if (tid == 0 && *s_err) {
+        atomicOr(P.status, *s_err);
+        *reinterpret_cast<volatile int*>(P.status_host) = *s_err;
+        __threadfence_system();
+    }
     if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(kTmemCols) : "memory");
 }
 
@@ -588,6 +593,8 @@ struct FusedWeights {
     uint8_t* d_b1 = nullptr;
     uint8_t* d_b2 = nullptr;
     int* d_status = nullptr;
+    int* h_status = nullptr;      // mapped pinned mirror of the status word
+    int* h_status_dev = nullptr;  // its device address
     bool attr_set = false;
 };
 
@@ -660,6 +667,9 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
     if (!fw.d_status) {
         if ((e = cudaMalloc(&fw.d_status, sizeof(int))) != cudaSuccess) return (int)e;
         if ((e = cudaMemset(fw.d_status, 0, sizeof(int))) != cudaSuccess) return (int)e;
+        if ((e = cudaHostAlloc(&fw.h_status, sizeof(int), cudaHostAllocMapped)) != cudaSuccess) return (int)e;
+        *fw.h_status = 0;
+        if ((e = cudaHostGetDevicePointer(&fw.h_status_dev, fw.h_status, 0)) != cudaSuccess) return (int)e;
     }
     if ((e = cudaMemcpy(fw.d_b1, b1.data(), kB1Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpy(fw.d_b2, b2.data(), kB2Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
@@ -674,23 +684,26 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
 
 inline void fused_free(FusedWeights& fw) {
     cudaFree(fw.d_b1); cudaFree(fw.d_b2); cudaFree(fw.d_status);
-    fw.d_b1 = fw.d_b2 = nullptr; fw.d_status = nullptr; fw.ready = false;
+    if (fw.h_status) cudaFreeHost(fw.h_status);
+    fw.d_b1 = fw.d_b2 = nullptr; fw.d_status = nullptr; fw.h_status = fw.h_status_dev = nullptr; fw.ready = false;
 }
 
-// One launch for n device-resident images.  Returns a cudaError_t as int (0 = launched).
-inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8_t* d_imgs, int64_t n, uint8_t* d_feats,
-                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
-    if (n <= 0) return 0;
-    if (n > 0x7fffffff || (reinterpret_cast<uintptr_t>(d_imgs) & 15)) return (int)cudaErrorInvalidValue;
-    CUtensorMap map;
+// Tensor map over n images [n][128][128] u8 at a device-accessible address (device memory or mapped pinned host memory).
+inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map) {
+    if (n <= 0 || n > 0x7fffffff || (reinterpret_cast<uintptr_t>(d_imgs) & 15) || !get_encode_tiled()) return (int)cudaErrorInvalidValue;
     const cuuint64_t gdim[3] = {128, 128, (cuuint64_t)n};
     const cuuint64_t gstride[2] = {128, 16384};
     const cuuint32_t box[3] = {(cuuint32_t)kInPitch, (cuuint32_t)kInRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode_tiled()(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_imgs), gdim, gstride, box, estr,
+    CUresult r = get_encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_imgs), gdim, gstride, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// One launch for the n images described by `map`.  Returns a cudaError_t as int (0 = launched).
+inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
+                            const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
     FusedParams P;
     std::memcpy(P.w0, fw.w0, sizeof(P.w0));
     std::memcpy(P.w0f, fw.w0f, sizeof(P.w0f));
@@ -698,20 +711,31 @@ inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8
     P.n_images = (int)n;
     P.b1 = fw.d_b1; P.b2 = fw.d_b2;
     P.out = d_feats; P.dump_l0 = dump_l0; P.dump_l1 = dump_l1;
-    P.status = fw.d_status;
+    P.status = fw.d_status; P.status_host = fw.h_status_dev;
     const int grid = (int)std::min<int64_t>(n, sm_count);
     conv_stack_fused_kernel<<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
     return (int)cudaGetLastError();
 }
 
-// Reads (and clears) the device status word; non-zero = a pipeline wait timed out inside some launch.
+// One launch for n device-resident images.
+inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8_t* d_imgs, int64_t n, uint8_t* d_feats,
+                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
+    if (n <= 0) return 0;
+    CUtensorMap map;
+    int rc = fused_encode_map(d_imgs, n, &map);
+    if (rc) return rc;
+    return launch_fused_map(fw, stream, map, n, d_feats, shifts, sm_count, dump_l0, dump_l1);
+}
+
+// Reads (and clears) the status word; non-zero = a pipeline wait timed out inside some launch.  The caller has
+// synchronised the stream, so the host-mapped mirror is current and no CUDA call is needed on the good path.
 inline int fused_poll_status(const FusedWeights& fw, int* bits) {
     *bits = 0;
-    if (!fw.d_status) return 0;
-    cudaError_t e = cudaMemcpy(bits, fw.d_status, sizeof(int), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return (int)e;
-    if (*bits) e = cudaMemset(fw.d_status, 0, sizeof(int));
-    return (int)e;
+    if (!fw.h_status) return 0;
+    *bits = *reinterpret_cast<volatile int*>(fw.h_status);
+    if (!*bits) return 0;
+    *fw.h_status = 0;
+    return (int)cudaMemset(fw.d_status, 0, sizeof(int));
 }
 
 }  // namespace cnnacc

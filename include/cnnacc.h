@@ -102,7 +102,9 @@ int cnnacc_wait(cnnacc_handle *h, int timeout_us);
 int cnnacc_read_features(cnnacc_handle *h, uint8_t *out, int n_ch, int ch_off);
 int cnnacc_read_feature_map(cnnacc_handle *h, int channel, int num_values, uint8_t *out);
 /* One image in, features out, lowest latency (FPGAEngine.run / ARMEngine.run shape,
- * realtime_detect.py:313-363,422-436).  Reports device time of the conv stack and of the readback. */
+ * realtime_detect.py:313-363,422-436).  128x128 runs zero-copy: the kernel reads the image from and writes the
+ * features to mapped pinned host memory (one launch + one sync).  conv_ms = wall time from the call to "done"
+ * (the reference times the same span with time.time(), realtime_detect.py:325-335); read_ms = the copy into feat. */
 int cnnacc_infer_one(cnnacc_handle *h, const uint8_t *img, uint8_t *feat, float *conv_ms, float *read_ms);
 
 /* ---- follow-on kernels: spatial-bin pool + linear + softmax + CAM bbox ---------------------
