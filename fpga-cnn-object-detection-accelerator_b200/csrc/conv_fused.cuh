@@ -25,17 +25,24 @@
 // The descriptor forms were verified on a B200 by tools/probe_umma.cu (profiles/r1_probe_umma_dp4a_tmem.txt) and are
 // replayed on the CPU by tests/test_packed_layouts.py.
 //
-// Warp roles (20 warps, 1 CTA/SM):
-//   warps 0-15   TMEM consumers: warp%4 = lane quarter, warp/4 = column quarter of every accumulator tile;
-//                tcgen05.ld -> pool -> shift/saturate -> act1 / act2 (smem) or CHW staging -> 16 KiB TMA store
+// Warp roles (21 warps, 1 CTA/SM):
+//   warps 0-15   TMEM consumers in 4 groups of 4 (warp%4 = TMEM lane quarter, warp/4 = group).  A group drains one
+//                accumulator job at a time: tcgen05.ld -> pool -> shift/saturate -> act1 / act2 (smem) or CHW staging
 //   warp 16      MMA issue (whole warp walks the schedule, one elected lane issues; operands in uniform registers)
 //   warp 17      TMA loads (weights once, then images)
 //   warps 18-19  Z builders (image -> layer-0 A operand)
-// Per image the MMA warp issues 14 jobs (8 x layer 0, 4 x layer 1, 2 x layer 2), each filling one 256-column half
-// of TMEM; consumers drain the halves in the same order, so every write-after-read on act1 / act2 is already
-// ordered by the job sequence and only the producer->consumer edges need barriers.
+//   warp 20      feature store (16 KiB cp.async.bulk per image from the staging buffer)
+// Schedule.  TMEM is four 128-column quarters Q0-Q3.  A layer-0 or layer-1 tile is a one-quarter job; a layer-2 block
+// (4 parities x 64 oc) takes Q0+Q1 ("region A") and is drained by two groups (32 oc each).  Per image k:
+//   phase L1(k):  8 layer-1 tile jobs rotating over Q2,Q3,Q0,Q1
+//   phase C(k):   layer 2 of image k in region A, issued in 8 chunks of 9 MMAs, INTERLEAVED with the 16 layer-0 tile
+//                 jobs of image k+1 ping-ponging on Q2/Q3 -- the tensor pipe chews on 432-cycle layer-2 chunks while the
+//                 consumers drain the (short-MMA, long-epilogue) layer-0 tiles.
+// Every write-after-read on act1 / act2 is ordered by the in-order completion of the MMA stream (a later job's
+// "full" barrier implies all earlier MMAs have finished reading), so only producer->consumer edges need barriers.
 #pragma once
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -74,18 +81,36 @@ constexpr int kOffBar   = kOffStage + kStageBytes;    // 228352
 constexpr int kFusedSmem = kOffBar + 256;             // 228608 <= 232448
 static_assert(kOffZ % 128 == 0 && kOffA1 % 128 == 0 && kOffA2 % 128 == 0 && kOffB0 % 128 == 0 && kOffStage % 128 == 0, "alignment");
 
+// Optional schedule trace (tools only, -DCNNACC_TRACE): CTA 0 records clock() at pipeline events into the spare
+// shared memory and prints them at exit.
+#ifdef CNNACC_TRACE
+constexpr int kTraceMax = 200;
+#define TRACE(role, code)                                                                                          \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && lane == 0 && trace_n < kTraceMax) {                                                 \
+            trace_buf[(role) * kTraceMax + trace_n] = ((unsigned)(code) << 24) | ((unsigned)clock64() & 0xFFFFFFu);   \
+            trace_n++;                                                                                             \
+        }                                                                                                          \
+    } while (0)
+#else
+#define TRACE(role, code) do { } while (0)
+#endif
+
 constexpr int kEpiWarps = 16, kZWarps = 2;
-constexpr int kWarpMma = kEpiWarps, kWarpTma = kWarpMma + 1, kWarpZ = kWarpTma + 1;
-constexpr int kFusedThreads = (kWarpZ + kZWarps) * 32;    // 640
+constexpr int kWarpMma = kEpiWarps, kWarpTma = kWarpMma + 1, kWarpZ = kWarpTma + 1, kWarpStore = kWarpZ + kZWarps;
+constexpr int kFusedThreads = (kWarpStore + 1) * 32;      // 672
 constexpr uint32_t kTmemCols = 512;
 
 // mbarrier slots (8 bytes each) at kOffBar
 enum : uint32_t {
     kBarInFull = 0, kBarInFree,                                     // TMA -> Z builders ; Z builders -> TMA
     kBarZReady, kBarZFree,                                          // Z builders -> MMA ; MMA (tcgen05.commit) -> Z builders
-    kBarA1TopReady, kBarA1BotReady,                                 // consumers -> MMA  (act1 rows 0-40 / all rows written)
+    kBarA1TopReady, kBarA1BotReady,                                 // consumers -> MMA  (act1 rows 0-36 / all rows written)
     kBarA2Ready,                                                    // consumers -> MMA  (act2 complete)
-    kBarTmFull0, kBarTmFull1, kBarTmEmpty0, kBarTmEmpty1,           // MMA -> consumers ; consumers -> MMA (TMEM halves)
+    kBarFullG0, kBarFullG1, kBarFullG2, kBarFullG3,                 // MMA -> consumer group g: "your next job is complete"
+    kBarEmptyQ0, kBarEmptyQ1, kBarEmptyQ2, kBarEmptyQ3,             // consumers -> MMA: quarter drained (4 warps = one group)
+    kBarEmptyA,                                                     // region A = Q0+Q1 drained (layer-2 job, 2 groups)
+    kBarStageFull, kBarStageFree,                                   // consumers -> store warp ; store warp -> consumers
     kBarW,                                                          // weights landed
     kNumBars
 };
@@ -220,6 +245,11 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform in the compiler's eyes
     const int n_local = (P.n_images - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // images of this CTA
+#ifdef CNNACC_TRACE
+    __shared__ unsigned trace_buf[2 * kTraceMax];
+    __shared__ int trace_cnt[3];
+    int trace_n = 0;
+#endif
 
     // ---- one-time setup ---------------------------------------------------------------------------------
     for (int i = tid; i < (kA1Alloc + kA2Bytes) / 16; i += kFusedThreads)                       // zero halos (and interiors)
@@ -229,8 +259,9 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         mbar_init(bar(kBarZReady), kZWarps); mbar_init(bar(kBarZFree), 1);
         mbar_init(bar(kBarA1TopReady), kEpiWarps); mbar_init(bar(kBarA1BotReady), kEpiWarps);
         mbar_init(bar(kBarA2Ready), kEpiWarps);
-        mbar_init(bar(kBarTmFull0), 1); mbar_init(bar(kBarTmFull1), 1);
-        mbar_init(bar(kBarTmEmpty0), kEpiWarps); mbar_init(bar(kBarTmEmpty1), kEpiWarps);
+        for (int i = 0; i < 4; i++) { mbar_init(bar(kBarFullG0 + i), 1); mbar_init(bar(kBarEmptyQ0 + i), 4); }
+        mbar_init(bar(kBarEmptyA), 8);
+        mbar_init(bar(kBarStageFull), kEpiWarps); mbar_init(bar(kBarStageFree), 1);
         mbar_init(bar(kBarW), 1);
         *s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -246,100 +277,108 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     auto wait_or_flag = [&](uint32_t b, uint32_t parity, int code) {
+        if (mbar_try(b, parity)) return;                 // fast path: already complete
         // ~0.1 s budget; once any wait has timed out every later wait gives up quickly so the CTA drains
         if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : 200000000LL)) atomicOr(s_err, code);
     };
 
     if (warp < kEpiWarps) {
         // =============== TMEM consumers ==========================================================================
-        const int q = warp & 3, c4 = warp >> 2;          // TMEM lane quarter (== warp % 4), column quarter
+        const int q = warp & 3, g = warp >> 2;           // TMEM lane quarter (== warp % 4), consumer group
         const int L = q * 32 + lane;
         const uint32_t t_lane = tm + ((uint32_t)(q * 32) << 16);
-        uint32_t uses[2] = {0, 0};                       // completed uses of each TMEM half (same sequence as the MMA warp)
-        for (int k = 0; k < n_local; k++) {
-            const int img = (int)blockIdx.x + k * (int)gridDim.x;
-            // ---- layer 0: 8 jobs x 2 tiles; tile t = pooled rows 4t..4t+3, TMEM lane = (row, column group) ----
-            // this warp: row 4t+q, window 2*lane + (c4>>1), channels 8*(c4&1) .. +7
-#pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                const int h = j & 1;
-                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
-                uses[h]++;
-                tc_fence_after();
-                const uint32_t taddr = t_lane + h * 256 + c4 * 32;
-                int va[16], vb[16], vc[16], vd[16];
-                tmem_ld16(taddr, va); tmem_ld16(taddr + 16, vb);                  // tile 2j
-                tmem_ld16(taddr + 128, vc); tmem_ld16(taddr + 144, vd);           // tile 2j+1
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
-                const int xp = 2 * lane + (c4 >> 1);
-                uint8_t* dst = smem + kOffA1 + ((xp + 1) & 1) * kA1Q + ((xp + 1) >> 1) * 16 + (c4 & 1) * 8;
-#pragma unroll
-                for (int tl = 0; tl < 2; tl++) {
-                    const int yp = 8 * j + 4 * tl + q;
-                    const uint2 w = tl ? pool_act_8ch(vc, vd, P.shift0) : pool_act_8ch(va, vb, P.shift0);
-                    *reinterpret_cast<uint2*>(dst + (yp + 1) * kA1P) = w;
-                    if (P.dump_l0) {                     // debug / register-protocol path: BRAM channels 0-15
-                        uint8_t* d = P.dump_l0 + (size_t)img * 65536 + (size_t)((c4 & 1) * 8) * 4096 + yp * 64 + xp;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) d[c * 4096] = (uint8_t)((c < 4 ? w.x : w.y) >> (8 * (c & 3)));
-                    }
-                }
-                if (j == 4 || j == 7) {                  // pooled rows 0-39 (act1 rows 0-40 cover the top tiles' 0-33) / all rows
-                    fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(j == 4 ? kBarA1TopReady : kBarA1BotReady));
-                }
-            }
-            // ---- layer 1: 4 jobs x 2 tiles of 128 pooling windows; this warp: channels 8*c4 .. +7 ----
-#pragma unroll 1
-            for (int j = 0; j < 4; j++) {
-                const int h = j & 1;
-                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
-                uses[h]++;
-                tc_fence_after();
-                const uint32_t taddr = t_lane + h * 256 + c4 * 32;
-                int va[16], vb[16], vc[16], vd[16];
-                tmem_ld16(taddr, va); tmem_ld16(taddr + 16, vb);
-                tmem_ld16(taddr + 128, vc); tmem_ld16(taddr + 144, vd);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
-#pragma unroll
-                for (int tl = 0; tl < 2; tl++) {
-                    const int t = 2 * j + tl;
-                    const int i = (t >> 2) * 16 + (L >> 3), jj = (t & 3) * 8 + (L & 7);
-                    const uint2 w = tl ? pool_act_8ch(vc, vd, P.shift1) : pool_act_8ch(va, vb, P.shift1);
-                    *reinterpret_cast<uint2*>(smem + kOffA2 + (c4 >> 1) * kA2C + (i + 1) * kA2P + ((jj + 1) & 1) * kA2Q +
-                                              ((jj + 1) >> 1) * 16 + (c4 & 1) * 8) = w;
-                    if (P.dump_l1) {                     // BRAM channels 16-47
-                        uint8_t* d = P.dump_l1 + (size_t)img * 32768 + (size_t)(c4 * 8) * 1024 + i * 32 + jj;
-#pragma unroll
-                        for (int c = 0; c < 8; c++) d[c * 1024] = (uint8_t)((c < 4 ? w.x : w.y) >> (8 * (c & 3)));
-                    }
-                }
-            }
+        // One warp's share of a job done: order the TMEM reads before the barrier and release the columns.
+        auto release = [&](uint32_t b) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b);
+        };
+        auto publish = [&](uint32_t b) {                 // smem written by this warp -> visible to the MMA (async proxy)
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarA2Ready));
-
-            // ---- layer 2: 2 jobs of 128 pooling windows x 4 parities; this warp: channels 16*c4 .. +15 ----
-            // -> staging (CHW) -> one 16 KiB TMA store
-            if (k > 0) {                                 // the previous image's store must have finished reading staging
-                if (warp == 0 && lane == 0) bulk_store_wait_read();
-                epi_bar_sync();
+            if (lane == 0) mbar_arrive(b);
+        };
+        // One "full" barrier per consumer group: the MMA warp commits each job to the group that owns it, so a group
+        // sees every phase of its barrier in order (a parity wait is only meaningful for the phase right after the
+        // last one the waiter has seen -- a barrier shared by groups that take turns would alias).
+        uint32_t my_jobs = 0;
+        auto wait_job = [&]() {
+            if (warp == 0) TRACE(1, 100);
+            wait_or_flag(bar(kBarFullG0 + g), my_jobs & 1, kErrMmaTimeout);
+            my_jobs++;
+            if (warp == 0) TRACE(1, 101);
+        };
+        // ---- layer-0 tile t (pooled rows 4t..4t+3) from quarter qi; TMEM lane = (row % 4, column group) ----
+        auto drain_l0 = [&](int img, int t, int qi) {
+            wait_job();
+            tc_fence_after();
+            const uint32_t taddr = t_lane + qi * 128;
+            const int yp = 4 * t + q;
+            uint8_t* rowp = smem + kOffA1 + (yp + 1) * kA1P;
+            uint2 w[4];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {       // two column quarters per pass (64 live accumulators)
+                int va[16], vb[16], vc[16], vd[16];
+                tmem_ld16(taddr + half * 64, va); tmem_ld16(taddr + half * 64 + 16, vb);
+                tmem_ld16(taddr + half * 64 + 32, vc); tmem_ld16(taddr + half * 64 + 48, vd);
+                tmem_ld_wait();
+                if (half == 1) { release(bar(kBarEmptyQ0 + qi)); if (warp == 0) TRACE(1, 102); }
+                w[2 * half] = pool_act_8ch(va, vb, P.shift0);
+                w[2 * half + 1] = pool_act_8ch(vc, vd, P.shift0);
             }
-#pragma unroll 1
-            for (int s = 0; s < 2; s++) {
-                const int h = s, j0 = s * 8;
-                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
-                uses[h]++;
-                tc_fence_after();
-                const int i = L >> 3, j = j0 + (L & 7);
-                const uint32_t taddr = t_lane + h * 256 + c4 * 16;
+            // column quarter cq = 2*w2 + och: window 2*lane + w2, channels 8*och..+7 -> one 16-byte vector per window
+            // window 2*lane -> halo column odd (plane 1, index lane); window 2*lane+1 -> even plane, index lane+1
+            *reinterpret_cast<uint4*>(rowp + kA1Q + lane * 16) = make_uint4(w[0].x, w[0].y, w[1].x, w[1].y);
+            *reinterpret_cast<uint4*>(rowp + (lane + 1) * 16) = make_uint4(w[2].x, w[2].y, w[3].x, w[3].y);
+            if (P.dump_l0) {                             // debug / register-protocol path: BRAM channels 0-15
+                uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    const uint2 e0 = w[c >> 3], e1 = w[2 + (c >> 3)];
+                    d[c * 4096] = (uint8_t)(((c & 4) ? e0.y : e0.x) >> (8 * (c & 3)));
+                    d[c * 4096 + 1] = (uint8_t)(((c & 4) ? e1.y : e1.x) >> (8 * (c & 3)));
+                }
+            }
+        };
+        // ---- layer-1 tile t (128 pooling windows) from quarter qi; columns = (oc/8)*32 + member*8 + oc%8 ----
+        auto drain_l1 = [&](int img, int t, int qi) {
+            wait_job();
+            tc_fence_after();
+            const uint32_t taddr = t_lane + qi * 128;
+            const int i = (t >> 2) * 16 + (L >> 3), jj = (t & 3) * 8 + (L & 7);
+            uint8_t* px = smem + kOffA2 + (i + 1) * kA2P + ((jj + 1) & 1) * kA2Q + ((jj + 1) >> 1) * 16;
+            uint2 w[4];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                int va[16], vb[16], vc[16], vd[16];
+                tmem_ld16(taddr + half * 64, va); tmem_ld16(taddr + half * 64 + 16, vb);
+                tmem_ld16(taddr + half * 64 + 32, vc); tmem_ld16(taddr + half * 64 + 48, vd);
+                tmem_ld_wait();
+                if (half == 1) release(bar(kBarEmptyQ0 + qi));
+                w[2 * half] = pool_act_8ch(va, vb, P.shift1);
+                w[2 * half + 1] = pool_act_8ch(vc, vd, P.shift1);
+            }
+            *reinterpret_cast<uint4*>(px) = make_uint4(w[0].x, w[0].y, w[1].x, w[1].y);              // channels 0-15
+            *reinterpret_cast<uint4*>(px + kA2C) = make_uint4(w[2].x, w[2].y, w[3].x, w[3].y);       // channels 16-31
+            if (P.dump_l1) {                             // BRAM channels 16-47
+                uint8_t* d = P.dump_l1 + (size_t)img * 32768 + i * 32 + jj;
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const uint2 e = w[c >> 3];
+                    d[c * 1024] = (uint8_t)(((c & 4) ? e.y : e.x) >> (8 * (c & 3)));
+                }
+            }
+        };
+        // ---- layer-2 block s, channel half hh (32 oc) from region A -> staging (CHW) ----
+        auto drain_l2 = [&](int s, int hh, bool wait_stage, uint32_t stage_par) {
+            wait_job();
+            tc_fence_after();
+            if (wait_stage) wait_or_flag(bar(kBarStageFree), stage_par, kErrSlotTimeout);   // previous image's store has read staging
+            const int i = L >> 3, j = s * 8 + (L & 7);
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                const int cg = 2 * hh + cc;              // group of 16 output channels
+                const uint32_t taddr = t_lane + cg * 16;
                 int m[16];
                 {
                     int v0[16], v1[16];
@@ -354,94 +393,152 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll
                     for (int c = 0; c < 16; c++) m[c] = max(m[c], max(v0[c], v1[c]));
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
-                uint8_t* o = smem + kOffStage + (c4 * 16) * 256 + i * 16 + j;
+                if (cc == 1) release(bar(kBarEmptyA));
+                uint8_t* o = smem + kOffStage + (cg * 16) * 256 + i * 16 + j;
 #pragma unroll
                 for (int c = 0; c < 16; c++) o[c * 256] = (uint8_t)act_u8(m[c], P.shift2);
             }
-            fence_async_smem();
-            epi_bar_sync();
-            if (warp == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+            publish(bar(kBarStageFull));
+        };
+
+        // phase P0: layer 0 of the first image, tile t -> quarter t%4, group t%4
+        {
+            const int img = (int)blockIdx.x;
+#pragma unroll 1
+            for (int m = 0; m < 4; m++) {
+                const int t = g + 4 * m;
+                drain_l0(img, t, g);
+                if (t <= 8 && t + 4 > 8) publish(bar(kBarA1TopReady));
+            }
+            publish(bar(kBarA1BotReady));
         }
-        if (warp == 0 && lane == 0) bulk_store_wait_all();
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            // phase L1(k): tile t -> group t%4, quarter (t+2)%4; this group: t = g, g+4
+#pragma unroll 1
+            for (int m = 0; m < 2; m++) drain_l1(img, g + 4 * m, (g + 2) & 3);
+            publish(bar(kBarA2Ready));
+            // phase C(k): layer 2 of image k (groups 0,1: block 0; groups 2,3: block 1), interleaved with layer 0 of image
+            // k+1 (tile t -> group t%4, quarter 2 + t%2); this group: t = g, g+4, g+8, g+12.  The order below is the order
+            // in which the MMA warp commits this group's jobs.
+            const int s = g >> 1, hh = g & 1;
+            if (k + 1 < n_local) {
+                const int img1 = img + (int)gridDim.x;
+#pragma unroll 1
+                for (int m = 0; m < 4; m++) {
+                    const int t = g + 4 * m;
+                    if (m == 2 && s == 0) drain_l2(0, hh, k > 0, (uint32_t)(k - 1) & 1);
+                    drain_l0(img1, t, 2 + (t & 1));
+                    if (t <= 8 && t + 4 > 8) publish(bar(kBarA1TopReady));
+                }
+                publish(bar(kBarA1BotReady));
+                if (s == 1) drain_l2(1, hh, k > 0, (uint32_t)(k - 1) & 1);
+            } else {
+                drain_l2(s, hh, k > 0, (uint32_t)(k - 1) & 1);
+            }
+        }
     } else if (warp == kWarpMma) {
         // =============== MMA issue: the whole warp walks the schedule, one elected lane issues ====================
         wait_or_flag(bar(kBarW), 0, kErrWeightTimeout);
-        uint32_t uses[2] = {0, 0};
         constexpr uint32_t idesc128 = umma_idesc_i8(128), idesc64 = umma_idesc_i8(64);
+        uint32_t nq0 = 0, nq1 = 0, nq2 = 0, nq3 = 0, nA = 0;      // jobs issued so far per quarter / region A
+        // wait until the previous job on a quarter (or region A) has been drained: completion #(n-1), trivially true for n = 0
+        auto wait_empty_q = [&](int qi, uint32_t n) { wait_or_flag(bar(kBarEmptyQ0 + qi), (n & 1) ^ 1, kErrEmptyTimeout); };
+        auto wait_empty_a = [&]() { wait_or_flag(bar(kBarEmptyA), (nA & 1) ^ 1, kErrEmptyTimeout); };
+        // layer-0 tile t of the image whose Z is resident -> quarter qi: ONE MMA (K = 32 is the whole patch), N = 128
+        auto issue_l0 = [&](int t, int qi, bool last) {      // owner group: t % 4
+            tc_fence_after();
+            if (elect_one()) {
+                // rows m = 32*(pooled row % 4) + column group: 8-row groups are 128 B apart, K half 1 is the next Z row
+                umma_i8(tm + qi * 128, umma_desc(s_base + kOffZ + (4 * t) * kZPitch, kZPitch, 128),
+                        umma_desc(s_base + kOffB0, 2048, 128), idesc128, 0);
+                umma_commit(bar(kBarFullG0 + (t & 3)));
+                if (last) umma_commit(bar(kBarZFree));
+            }
+            __syncwarp();
+        };
+        // layer-1 tile t (row half t/4, column block t%4) -> quarter qi: 8 Toeplitz K-slabs, N = 128
+        auto issue_l1 = [&](int t, int qi) {                 // owner group: t % 4
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t a0 = umma_desc(s_base + kOffA1 + (32 * (t >> 2)) * kA1P + (8 * (t & 3)) * 16, kA1Q, 2 * kA1P);
+                const uint64_t b0 = umma_desc(s_base + kOffB1, 2048, 128);
+#pragma unroll
+                for (int sl = 0; sl < 8; sl++) {
+                    const int r = sl >> 1, sx = sl & 1;
+                    umma_i8(tm + qi * 128, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), b0 + (uint64_t)((sl * kB1Slab) >> 4), idesc128, sl > 0);
+                }
+                umma_commit(bar(kBarFullG0 + (t & 3)));
+            }
+            __syncwarp();
+        };
+        // layer-2 block s, parity p (one of four 64-column accumulators of region A): 9 taps, N = 64
+        auto issue_l2_chunk = [&](int s, int p) {
+            tc_fence_after();
+            if (elect_one()) {
+                const int a = p >> 1, b = p & 1;
+                const uint64_t a0 = umma_desc(s_base + kOffA2 + (s * 8) * 16, kA2C, 2 * kA2P);
+                const uint64_t b0 = umma_desc(s_base + kOffB2, 1024, 128);
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const int dy = t / 3, dx = t % 3;
+                    const int aoff = (a + dy) * kA2P + ((b + dx) & 1) * kA2Q + ((b + dx) >> 1) * 16;
+                    umma_i8(tm + p * 64, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)((t * 2048) >> 4), idesc64, t > 0);
+                }
+                if (p == 3) { umma_commit(bar(kBarFullG0 + 2 * s)); umma_commit(bar(kBarFullG0 + 2 * s + 1)); }   // owners: groups 2s, 2s+1
+            }
+            __syncwarp();
+        };
+
+        // phase P0: layer 0 of the first image, tile t -> quarter t%4
+        TRACE(0, 1);
+        wait_or_flag(bar(kBarZReady), 0, kErrZTimeout);
+        TRACE(0, 2);
+#pragma unroll 1
+        for (int t = 0; t < 16; t++) {
+            const int qi = t & 3;
+            const uint32_t n = (qi == 0) ? nq0 : (qi == 1) ? nq1 : (qi == 2) ? nq2 : nq3;
+            wait_empty_q(qi, n);
+            issue_l0(t, qi, t == 15);
+            if (qi == 0) nq0++; else if (qi == 1) nq1++; else if (qi == 2) nq2++; else nq3++;
+        }
         for (int k = 0; k < n_local; k++) {
-            // ---- layer 0: 8 jobs x 2 tiles, ONE MMA per tile (K = 32 is the whole patch), N = 128 ----
-            wait_or_flag(bar(kBarZReady), (uint32_t)k & 1, kErrZTimeout);
+            // phase L1(k): tile t -> quarter (t+2)%4 (Q2,Q3 first: region A may still be draining layer 2 of image k-1)
 #pragma unroll 1
-            for (int j = 0; j < 8; j++) {
-                const int h = j & 1;
-                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
-                uses[h]++;
-                tc_fence_after();
-                if (elect_one()) {
-                    // rows m = 32*(pooled row % 4) + column group: 8-row groups are 128 B apart, K half 1 is the next Z row
-                    const uint64_t a0 = umma_desc(s_base + kOffZ + (8 * j) * kZPitch, kZPitch, 128);
-                    const uint64_t b0 = umma_desc(s_base + kOffB0, 2048, 128);
-                    umma_i8(tm + h * 256, a0, b0, idesc128, 0);
-                    umma_i8(tm + h * 256 + 128, a0 + (uint64_t)((4 * kZPitch) >> 4), b0, idesc128, 0);
-                    umma_commit(bar(kBarTmFull0 + h));
-                    if (j == 7) umma_commit(bar(kBarZFree));
-                }
-                __syncwarp();
+            for (int t = 0; t < 8; t++) {
+                const int qi = (t + 2) & 3;
+                if (t == 0) { TRACE(0, 10); wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout); TRACE(0, 11); }
+                if (t == 4) { TRACE(0, 12); wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout); TRACE(0, 13); }
+                const uint32_t n = (qi == 0) ? nq0 : (qi == 1) ? nq1 : (qi == 2) ? nq2 : nq3;
+                TRACE(0, 50);
+                wait_empty_q(qi, n);
+                if (qi < 2) wait_empty_a();              // Q0/Q1 were last used by a layer-2 job
+                TRACE(0, 20 + t);
+                issue_l1(t, qi);
+                TRACE(0, 52);
+                if (qi == 0) nq0++; else if (qi == 1) nq1++; else if (qi == 2) nq2++; else nq3++;
             }
-            // ---- layer 1: 4 jobs x 2 tiles (2 row halves x 4 column blocks) x 8 K-slabs, N = 128 ----
+            const bool more = (k + 1 < n_local);
+            // phase C(k): layer 2 of image k in region A, 8 chunks, interleaved with layer 0 of image k+1 on Q2/Q3
+            TRACE(0, 30);
+            if (more) wait_or_flag(bar(kBarZReady), (uint32_t)(k + 1) & 1, kErrZTimeout);
+            TRACE(0, 31);
 #pragma unroll 1
-            for (int j = 0; j < 4; j++) {
-                const int h = j & 1;
-                if (j == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
-                if (j == 2) wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
-                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
-                uses[h]++;
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t b0 = umma_desc(s_base + kOffB1, 2048, 128);
-#pragma unroll
-                    for (int tl = 0; tl < 2; tl++) {
-                        const int t = 2 * j + tl, ty = t >> 2, tx = t & 3;
-                        const uint32_t d = tm + h * 256 + tl * 128;
-                        const uint64_t a0 = umma_desc(s_base + kOffA1 + (32 * ty) * kA1P + (8 * tx) * 16, kA1Q, 2 * kA1P);
-#pragma unroll
-                        for (int sl = 0; sl < 8; sl++) {
-                            const int r = sl >> 1, sx = sl & 1;
-                            umma_i8(d, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), b0 + (uint64_t)((sl * kB1Slab) >> 4), idesc128, sl > 0);
-                        }
-                    }
-                    umma_commit(bar(kBarTmFull0 + h));
+            for (int c = 0; c < 8; c++) {
+                const int s = c >> 2, p = c & 3;
+                if (more) {
+                    TRACE(0, 60);
+                    wait_empty_q(2, nq2); TRACE(0, 61); issue_l0(2 * c, 2, false); nq2++;
+                    TRACE(0, 62);
+                    wait_empty_q(3, nq3); TRACE(0, 63); issue_l0(2 * c + 1, 3, c == 7); nq3++;
+                    TRACE(0, 64);
                 }
-                __syncwarp();
-            }
-            // ---- layer 2: 2 jobs x 4 parities x 9 taps, N = 64 ----
-            wait_or_flag(bar(kBarA2Ready), (uint32_t)k & 1, kErrAct2Timeout);
-#pragma unroll 1
-            for (int s = 0; s < 2; s++) {
-                const int h = s, j0 = s * 8;
-                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
-                uses[h]++;
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t a0 = umma_desc(s_base + kOffA2 + j0 * 16, kA2C, 2 * kA2P);
-                    const uint64_t b0 = umma_desc(s_base + kOffB2, 1024, 128);
-#pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        const int a = p >> 1, b = p & 1;
-                        const uint32_t d = tm + h * 256 + p * 64;
-#pragma unroll
-                        for (int t = 0; t < 9; t++) {
-                            const int dy = t / 3, dx = t % 3;
-                            const int aoff = (a + dy) * kA2P + ((b + dx) & 1) * kA2Q + ((b + dx) >> 1) * 16;
-                            umma_i8(d, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)((t * 2048) >> 4), idesc64, t > 0);
-                        }
-                    }
-                    umma_commit(bar(kBarTmFull0 + h));
-                }
-                __syncwarp();
+                if (c == 0) { TRACE(0, 32); wait_or_flag(bar(kBarA2Ready), (uint32_t)k & 1, kErrAct2Timeout); TRACE(0, 33); }
+                if (p == 0) { wait_empty_a(); wait_empty_q(0, nq0); wait_empty_q(1, nq1); }
+                TRACE(0, 40 + c);
+                issue_l2_chunk(s, p);
+                TRACE(0, 70);
+                if (p == 3) nA++;
             }
         }
     } else if (warp == kWarpTma) {
@@ -459,7 +556,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp < kWarpStore) {
         // =============== Z builders: image -> layer-0 A operand ===================================================
         // Z[j][xg] (16 B) = image rows 2j-1 and 2j, columns 4*xg-1 .. 4*xg+6 (8 B each); out-of-image bytes are 0.
         const int zw = warp - kWarpZ;
@@ -483,11 +580,34 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar(kBarZReady)); mbar_arrive(bar(kBarInFree)); }
         }
+    } else {
+        // =============== feature store: one 16 KiB bulk copy per image ============================================
+        for (int k = 0; k < n_local; k++) {
+            wait_or_flag(bar(kBarStageFull), (uint32_t)k & 1, kErrSlotTimeout);
+            if (lane == 0) {
+                bulk_store(P.out + (size_t)((int)blockIdx.x + k * (int)gridDim.x) * 16384, s_base + kOffStage, kStageBytes);
+                bulk_store_wait_read();
+                mbar_arrive(bar(kBarStageFree));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) bulk_store_wait_all();
+        __syncwarp();
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------
+#ifdef CNNACC_TRACE
+    if (blockIdx.x == 0 && lane == 0 && (warp == kWarpMma || warp == 0)) trace_cnt[warp == 0 ? 1 : 0] = trace_n;
+#endif
     tc_fence_before();
     __syncthreads();
+#ifdef CNNACC_TRACE
+    if (blockIdx.x == 0 && tid == 0) {
+        for (int r = 0; r < 2; r++)
+            for (int i = 0; i < trace_cnt[r]; i++)
+                printf("TRACE %d %d %u\n", r, (int)(trace_buf[r * kTraceMax + i] >> 24), trace_buf[r * kTraceMax + i] & 0xFFFFFFu);
+    }
+#endif
     if (tid == 0 && *s_err) {
         atomicOr(P.status, *s_err);
         *reinterpret_cast<volatile int*>(P.status_host) = *s_err;
