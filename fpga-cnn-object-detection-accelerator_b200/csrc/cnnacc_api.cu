@@ -276,10 +276,10 @@ int cnnacc_set_shifts(cnnacc_handle* h, int s0, int s1, int s2) {
     return CNNACC_OK;
 }
 
-int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint8_t* b0, uint8_t* b1, uint8_t* b2) {
-    if (!weights_bin || !b0 || !b1 || !b2 || n != CNNACC_WEIGHT_BYTES) return CNNACC_ERR_ARG;
-    static_assert(CNNACC_PACK_B0_BYTES == kB0Bytes && CNNACC_PACK_B1_BYTES == kB1Bytes && CNNACC_PACK_B2_BYTES == kB2Bytes, "header out of date");
-    fused_pack_weights(weights_bin, b0, b1, b2);
+int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint32_t* w0, uint8_t* b1, uint8_t* b2) {
+    if (!weights_bin || !w0 || !b1 || !b2 || n != CNNACC_WEIGHT_BYTES) return CNNACC_ERR_ARG;
+    static_assert(CNNACC_PACK_B1_BYTES == kB1Bytes && CNNACC_PACK_B2_BYTES == kB2Bytes, "header out of date");
+    fused_pack_weights(weights_bin, reinterpret_cast<uint32_t(*)[6]>(w0), reinterpret_cast<uint32_t(*)[32]>(w0 + 96), b1, b2);
     return CNNACC_OK;
 }
 

@@ -5,46 +5,35 @@
 // (rtl/core/cnn_acc_top.v).  Like the FPGA design, every intermediate map stays on chip: one CTA per SM
 // keeps an image's maps in shared memory and HBM sees 16 KiB of pixels in and 16 KiB of features out.
 //
-// All three layers run as int8 implicit GEMM on tcgen05 (A = u8 activations, B = s8 weights, D = s32 in TMEM),
-// each followed by >>shift, ReLU/saturate (arm_cnn.c:127-135) and 2x2 max-pool (arm_cnn.c:115-143), pooled on
-// the raw s32 first (monotone activation).  No im2col is materialised for layers 1-2: the
-// activation maps are stored as [y+1][x-parity][(x+1)/2][16 ch] bytes with a zero halo, so a no-swizzle K-major
-// UMMA core matrix (8 rows x 16 B) is "8 same-parity pixels x 16 channels", a conv tap is a 16-byte-granular
-// descriptor start offset, and SBO = 2 row pitches makes the 128 rows of an MMA a 16-row-pair x 8-column-pair block.
+//   layer 0  (1->16, 128x128, K=9)    CUDA cores: dp4a.u32.s32, 2x2 pool in registers, -> act1 (smem)
+//   layer 1  (16->32, 64x64, K=144)   tcgen05.mma kind::i8 (A = u8 activations, B = s8 weights, D = s32 in TMEM)
+//   layer 2  (32->64, 32x32, K=288)   tcgen05.mma kind::i8
+//   each followed by >>shift, ReLU/saturate (arm_cnn.c:127-135) and 2x2 max-pool (arm_cnn.c:115-143),
+//   pooled on the raw s32 first (monotone activation).
 //
-//   layer 0  (1->16, K=9)    one MMA row = TWO adjacent 2x2 pooling windows; K = 32 = their shared 4-row x 8-column
-//            patch, re-laid out once per image by two "Z" warps as Z[row pair j][column group][rows 2j-1,2j x 8 cols];
-//            N = 128 = 2 windows x 4 members x 16 oc, B = the 3x3 kernel Toeplitz-expanded over the patch.  ONE
-//            MMA (64 clk) yields 256 pooled pixels x 16 oc.  (History: dp4a 16.4 M img/s -- IDP pipe saturated;
-//            mma.sync 17.9 M -- legacy IMMA is 1/4 of the tcgen05 rate and shares its pipe; see DESIGN.md.)
-//   layer 1  (16->32, K=144) one MMA row = one pooling window; N = 128 = 4 members x 32 oc, B Toeplitz-expanded over
-//            the window's 4x4 patch: 8 K-slabs of (2 adjacent pixels x 16 ch), LBO = parity-plane stride.
-//   layer 2  (32->64, K=288) one MMA row = one output pixel of ONE parity (y%2, x%2); K = 32 = one tap over both
-//            16-channel planes (LBO = plane stride), 9 MMAs, N = 64; the four parities go to four TMEM column groups.
-//   In every layer all four members of a pooling window land in ONE TMEM lane: the pool is thread-local.
-// The descriptor forms were verified on a B200 by tools/probe_umma.cu (profiles/r1_probe_umma_dp4a_tmem.txt) and are
-// replayed on the CPU by tests/test_packed_layouts.py.
+// Implicit GEMM without im2col.  Activation maps are stored as [y+1][x-parity][(x+1)/2][16 ch] bytes with a
+// zero halo, so a no-swizzle K-major UMMA core matrix (8 rows x 16 B) is "8 same-parity pixels x 16 channels",
+// a conv tap is a 16-byte-granular start-address offset, and SBO = 2 row pitches makes the 128 rows of an MMA
+// a block of 16 row-pairs x 8 column-pairs.
+//   layer 1: one MMA row = one 2x2 POOLING WINDOW.  N = 128 = 4 window members x 32 out-channels, and the B
+//            operand is the 3x3 kernel Toeplitz-expanded over the window's 4x4 input patch: 8 K-slabs of
+//            (2 adjacent pixels x 16 ch), LBO = parity-plane stride.  8 MMAs per 128 windows (56 % of the MAC
+//            slots are useful, but an i8 MMA costs the same ~77 clk for any N <= 128 -- profiles/
+//            r1_probe_umma_dp4a_tmem.txt -- so this is 2.5x fewer tensor cycles than N = 32 per tap pair).
+//            All four members of a window land in one TMEM lane: the pool is thread-local.
+//   layer 2: one MMA row = one output pixel of ONE parity (y%2, x%2); K=32 = one tap over both 16-channel
+//            planes (LBO = plane stride), 9 MMAs, N = 64; the four parities go to four TMEM column groups.
+// These descriptor forms were verified on a B200 by tools/probe_umma.cu (profiles/r1_probe_umma_dp4a_tmem.txt).
 //
-// Warp roles (22 warps, 1 CTA/SM):
-//   warps 0-15   TMEM consumers in 4 groups of 4 (warp%4 = TMEM lane quarter, warp/4 = group).  A group drains one
-//                accumulator job at a time: tcgen05.ld -> pool -> shift/saturate -> act1 / act2 (smem) or CHW staging
-//   warp 16      issuer A: layer-1 tiles (ping-pong on TMEM quarters Q0/Q1) + layer-2 block 0 (region A = Q0+Q1);
-//                its jobs are drained by groups 0,1
-//   warp 17      issuer B: layer-0 tile pairs (Q2/Q3) + layer-2 block 1 (region B = Q2+Q3); drained by groups 2,3
-//   warp 18      TMA loads (weights once, then images)
-//   warps 19-20  Z builders (image -> layer-0 A operand)
-//   warp 21      feature store (16 KiB cp.async.bulk per image from the staging buffer)
-// Why two issuers: a kind::i8 MMA here lasts only 48-64 clk and the tcgen05 queue is shallow, so one issuing thread
-// cannot hide its per-job bookkeeping (barrier waits ~100 clk each) behind its own MMAs -- measured: tensor pipe 43 %
-// busy with a single issuer (tools/trace_run.py).  With two independent streams each issuer's bookkeeping overlaps
-// the other's MMAs.  Every barrier has exactly one kind of waiter that observes all of its phases in order (a parity
-// wait is only meaningful for the phase right after the last one the waiter has seen): each TMEM region is owned by
-// one issuer, each consumer group is fed by one issuer.  Cross-stream hazards are explicit:
-//   act1 write-after-read  layer-0 drains of image k+1 wait for L1TopDone(k) / L1Done(k) (tcgen05.commit by issuer A)
-//   act2 write-after-read  layer-1 drains of image k+1 wait for L2DoneB(k) (issuer B); block 0 is in-order on issuer A
+// Warp roles (18 warps, 1 CTA/SM).  The dp4a pipe (layer 0) and the tensor pipe (layers 1-2) run concurrently
+// on DIFFERENT images: while the tensor core and the epilogue warps finish image k, the layer-0 warps already
+// produce image k+1 into the half of act1 the MMAs have released.
+//   warps 0-7    layer 0 (dp4a) : input slot -> act1
+//   warps 8-15   epilogues      : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
+//   warp 16      MMA issue (one elected thread), TMEM allocation
+//   warp 17      TMA loads (weights once, then images two ahead)
 #pragma once
 #include <cuda.h>
-#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -53,10 +42,11 @@
 namespace cnnacc {
 
 // ---- shared-memory plan (bytes) ---------------------------------------------------------------------
-constexpr int kInRows    = 130;                       // image rows -1 .. 128 (TMA box 128 x 130, OOB rows zero-filled)
-constexpr int kInBytes   = 128 * kInRows;             // 16640, one TMA transaction
-constexpr int kZPitch    = 512;                       // Z row = 32 column groups x 16 B
-constexpr int kZBytes    = 65 * kZPitch;              // 33280: row pairs (2j-1, 2j), j = 0..64
+constexpr int kInPitch   = 160;                       // x = -16 .. 143 (TMA box, OOB zero-filled; the innermost
+                                                      // box coordinate must be 16-byte aligned: tools/probe_tma.cu)
+constexpr int kInRows    = 130;                       // y = -1 .. 128
+constexpr int kInBytes   = kInPitch * kInRows;        // 20800, one TMA transaction
+constexpr int kInStride  = 20864;                     // 128-byte aligned slot size
 constexpr int kA1Q       = 33 * 16;                   // act1 parity-plane stride   (528)
 constexpr int kA1P       = 2 * kA1Q;                  // act1 row pitch             (1056)
 constexpr int kA1Bytes   = 66 * kA1P;                 // 69696
@@ -65,69 +55,58 @@ constexpr int kA2Q       = 17 * 16;                   // act2 parity-plane strid
 constexpr int kA2P       = 2 * kA2Q;                  // act2 row pitch             (544)
 constexpr int kA2C       = 34 * kA2P;                 // act2 channel-block plane   (18496)
 constexpr int kA2Bytes   = 2 * kA2C;                  // 36992
-constexpr int kB0Bytes   = 4096;                      // layer-0 B: K=32 x N=128
 constexpr int kB1Slab    = 4096;                      // layer-1 B: one K=32 slab x N=128
 constexpr int kB1Bytes   = 8 * kB1Slab;               // 8 slabs (4 patch rows x 2 column pairs)
 constexpr int kB2Bytes   = 9 * 2048;                  // layer-2 B: 9 taps x (2 K-halves x 8 row groups x 128 B)
 constexpr int kStageBytes = 16384;                    // one image's features, CHW, for the TMA store
 
-constexpr int kOffIn    = 0;
-constexpr int kOffZ     = kInBytes;                   // 16640
-constexpr int kOffA1    = kOffZ + kZBytes;            // 49920
-constexpr int kOffA2    = kOffA1 + kA1Alloc;          // 119680
-constexpr int kOffB0    = kOffA2 + kA2Bytes;          // 156672
-constexpr int kOffB1    = kOffB0 + kB0Bytes;          // 160768
-constexpr int kOffB2    = kOffB1 + kB1Bytes;          // 193536
-constexpr int kOffStage = kOffB2 + kB2Bytes;          // 211968
-constexpr int kOffBar   = kOffStage + kStageBytes;    // 228352
-constexpr int kFusedSmem = kOffBar + 256;             // 228608 <= 232448
-static_assert(kOffZ % 128 == 0 && kOffA1 % 128 == 0 && kOffA2 % 128 == 0 && kOffB0 % 128 == 0 && kOffStage % 128 == 0, "alignment");
+constexpr int kOffIn0   = 0;
+constexpr int kOffIn1   = kInStride;
+constexpr int kOffA1    = 2 * kInStride;              // 41728
+constexpr int kOffA2    = kOffA1 + kA1Alloc;          // 111488
+constexpr int kOffB1    = kOffA2 + kA2Bytes;          // 148480
+constexpr int kOffB2    = kOffB1 + kB1Bytes;          // 181248
+constexpr int kOffStage = kOffB2 + kB2Bytes;          // 199680
+constexpr int kOffBar   = kOffStage + kStageBytes;    // 216064
+constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
 
-// Optional schedule trace (tools only, -DCNNACC_TRACE): CTA 0 records clock() at pipeline events into the spare
-// shared memory and prints them at exit.
-#ifdef CNNACC_TRACE
-constexpr int kTraceMax = 240;
-#define TRACE(role, code)                                                                                          \
-    do {                                                                                                           \
-        if (blockIdx.x == 0 && lane == 0 && trace_n < kTraceMax) {                                                 \
-            trace_buf[(role) * kTraceMax + trace_n] = ((unsigned)(code) << 24) | ((unsigned)clock64() & 0xFFFFFFu);   \
-            trace_n++;                                                                                             \
-        }                                                                                                          \
-    } while (0)
-#else
-#define TRACE(role, code) do { } while (0)
+#ifndef CNNACC_L0_DP4A
+#define CNNACC_L0_DP4A 0      // 1 = layer 0 on the dp4a pipe (the first design; kept for the ablation in profiles/)
 #endif
-
-constexpr int kEpiWarps = 16, kZWarps = 2;
-constexpr int kWarpMmaA = kEpiWarps, kWarpMmaB = kWarpMmaA + 1, kWarpTma = kWarpMmaB + 1, kWarpZ = kWarpTma + 1,
-              kWarpStore = kWarpZ + kZWarps;
-constexpr int kFusedThreads = (kWarpStore + 1) * 32;      // 704
+#ifndef CNNACC_L0_WARPS
+#define CNNACC_L0_WARPS 16
+#endif
+#ifndef CNNACC_EPI_WARPS
+#define CNNACC_EPI_WARPS 4
+#endif
+constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
+static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
+constexpr int kWarpMma = kL0Warps + kEpiWarps, kWarpTma = kWarpMma + 1;
+constexpr int kFusedThreads = (kWarpTma + 1) * 32;    // 576
 constexpr uint32_t kTmemCols = 512;
 
 // mbarrier slots (8 bytes each) at kOffBar
 enum : uint32_t {
-    kBarInFull = 0, kBarInFree,                                     // TMA -> Z builders ; Z builders -> TMA
-    kBarZReady, kBarZFree,                                          // Z builders -> issuer B ; issuer B (commit) -> Z builders
-    kBarA1TopReady, kBarA1BotReady,                                 // groups 2,3 -> issuer A  (act1 rows 0-36 / all rows written)
-    kBarA2Ready,                                                    // groups 0,1 -> issuers A and B (act2 complete)
-    kBarL1TopDone, kBarL1Done,                                      // issuer A (commit) -> groups 2,3: act1 rows 0-33 / all rows free
-    kBarL2DoneB,                                                    // issuer B (commit) -> groups 0,1: act2 free
-    kBarFullG0, kBarFullG1, kBarFullG2, kBarFullG3,                 // issuer -> consumer group g: "your next job is complete"
-    kBarEmptyQ0, kBarEmptyQ1, kBarEmptyQ2, kBarEmptyQ3,             // group -> issuer: quarter drained (4 warps)
-    kBarEmptyA, kBarEmptyB,                                         // groups 0,1 / 2,3 -> issuer: layer-2 block drained (8 warps)
-    kBarStageFull, kBarStageFree,                                   // consumers -> store warp ; store warp -> consumers
+    kBarInFull0 = 0, kBarInFull1, kBarInFree0, kBarInFree1,        // TMA -> layer 0 ; layer 0 -> TMA
+    kBarA1TopReady, kBarA1BotReady,                                 // layer 0 -> MMA  (act1 rows 0-33 / all rows written)
+    kBarA1TopFree, kBarA1BotFree,                                   // MMA (tcgen05.commit) -> layer 0
+    kBarTmFull0, kBarTmFull1, kBarTmEmpty0, kBarTmEmpty1,           // MMA -> epilogue ; epilogue -> MMA (TMEM halves)
+    kBarA2Ready,                                                    // epilogue -> MMA (act2 complete)
     kBarW,                                                          // weights landed
     kNumBars
 };
 
 // error bits reported through the status word
 constexpr int kErrInputTimeout = 1, kErrMmaTimeout = 2, kErrEmptyTimeout = 4, kErrWeightTimeout = 8,
-              kErrAct1Timeout = 16, kErrAct2Timeout = 32, kErrSlotTimeout = 64, kErrZTimeout = 128;
+              kErrAct1Timeout = 16, kErrAct2Timeout = 32, kErrSlotTimeout = 64;
 
 struct FusedParams {
+    uint32_t w0[16][6];          // layer-0 dp4a words per out-channel: lo[dy], hi[dy]  (constant bank; CNNACC_L0_DP4A build)
+    uint32_t w0f[8][32];         // layer-0 mma.sync B fragments: [block = py*4 + ol][lane]
     int shift0, shift1, shift2;
     int n_images;
-    const uint8_t* b012;         // packed B operands, layer 0 | layer 1 | layer 2 (kB0Bytes + kB1Bytes + kB2Bytes)
+    const uint8_t* b1;           // packed layer-1 B operand (kB1Bytes)
+    const uint8_t* b2;           // packed layer-2 B operand (kB2Bytes)
     uint8_t* out;                // [n][64][16][16]
     uint8_t* dump_l0;            // optional [n][16][64][64]
     uint8_t* dump_l1;            // optional [n][32][32][32]
@@ -197,11 +176,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 3D tiled TMA load (x, y, image) -> smem, completion on an mbarrier.  Box origin y = -1: the top / bottom padding
-// rows arrive zero-filled.
+// 3D tiled TMA load (x, y, image) -> smem, completion on an mbarrier.
 __device__ __forceinline__ void tma_load_image(uint32_t dst, const CUtensorMap* map, uint32_t bar, int img) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 :: "r"(dst), "l"(map), "r"(0), "r"(-1), "r"(img), "r"(bar) : "memory");
+                 :: "r"(dst), "l"(map), "r"(-16), "r"(-1), "r"(img), "r"(bar) : "memory");
 }
 // 1D bulk copy global -> smem (pre-packed weights).
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -217,23 +195,19 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory"); }
 
+// Warp-level int8 MMA for layer 0 (K = 9 is too thin for a 128-row tcgen05 tile without a re-layout pass):
+// D(16x8,s32) += A(16x16,u8) * B(16x8,s8).  Fragments (lane = 4*g + t): a0/a1 = rows g / g+8, k = 4t..4t+3;
+// b0 = k 4t..4t+3 of column g; c0,c1 = row g cols 2t,2t+1; c2,c3 = row g+8.  SASS: IMMA.16816.U8.S8.
+__device__ __forceinline__ void imma_16816(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
 // arm_cnn.c:127-135 for one accumulator: shift, then saturate to [0,255] (negatives stay negative under >>).
 __device__ __forceinline__ uint32_t act_u8(int v, int shift) {
     uint32_t d;
     asm("cvt.sat.u8.s32 %0, %1;" : "=r"(d) : "r"(v >> shift));
     return d;
-}
-
-// Pool the four window members held in one TMEM lane and activate: cols [taddr, +32) = 4 members x 8 channels.
-// Returns the 8 channels packed into two words (arm_cnn.c:115-143 pool, :127-135 activation).
-__device__ __forceinline__ uint2 pool_act_8ch(const int (&v0)[16], const int (&v1)[16], int shift) {
-    int m[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) m[c] = max4(v0[c], v0[8 + c], v1[c], v1[8 + c]);
-    uint2 w;
-    w.x = act_pack4(m[0], m[1], m[2], m[3], shift);
-    w.y = act_pack4(m[4], m[5], m[6], m[7], shift);
-    return w;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
@@ -250,29 +224,23 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform in the compiler's eyes
     const int n_local = (P.n_images - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // images of this CTA
-#ifdef CNNACC_TRACE
-    __shared__ unsigned trace_buf[2 * kTraceMax];
-    __shared__ int trace_cnt[3];
-    int trace_n = 0;
-#endif
 
     // ---- one-time setup ---------------------------------------------------------------------------------
     for (int i = tid; i < (kA1Alloc + kA2Bytes) / 16; i += kFusedThreads)                       // zero halos (and interiors)
         reinterpret_cast<uint4*>(smem + kOffA1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        mbar_init(bar(kBarInFull), 1); mbar_init(bar(kBarInFree), kZWarps);
-        mbar_init(bar(kBarZReady), kZWarps); mbar_init(bar(kBarZFree), 1);
-        mbar_init(bar(kBarA1TopReady), 8); mbar_init(bar(kBarA1BotReady), 8);
-        mbar_init(bar(kBarA2Ready), 8);
-        mbar_init(bar(kBarL1TopDone), 1); mbar_init(bar(kBarL1Done), 1); mbar_init(bar(kBarL2DoneB), 1);
-        for (int i = 0; i < 4; i++) { mbar_init(bar(kBarFullG0 + i), 1); mbar_init(bar(kBarEmptyQ0 + i), 4); }
-        mbar_init(bar(kBarEmptyA), 8); mbar_init(bar(kBarEmptyB), 8);
-        mbar_init(bar(kBarStageFull), kEpiWarps); mbar_init(bar(kBarStageFree), 1);
+        mbar_init(bar(kBarInFull0), 1); mbar_init(bar(kBarInFull1), 1);
+        mbar_init(bar(kBarInFree0), kL0Warps); mbar_init(bar(kBarInFree1), kL0Warps);
+        mbar_init(bar(kBarA1TopReady), kL0Warps); mbar_init(bar(kBarA1BotReady), kL0Warps);
+        mbar_init(bar(kBarA1TopFree), 1); mbar_init(bar(kBarA1BotFree), 1);
+        mbar_init(bar(kBarTmFull0), 1); mbar_init(bar(kBarTmFull1), 1);
+        mbar_init(bar(kBarTmEmpty0), kEpiWarps); mbar_init(bar(kBarTmEmpty1), kEpiWarps);
+        mbar_init(bar(kBarA2Ready), kEpiWarps);
         mbar_init(bar(kBarW), 1);
         *s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kWarpMmaA) {
+    if (warp == kWarpMma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -288,351 +256,343 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : 200000000LL)) atomicOr(s_err, code);
     };
 
-    if (warp < kEpiWarps) {
-        // =============== TMEM consumers ==========================================================================
-        const int q = warp & 3, g = warp >> 2;           // TMEM lane quarter (== warp % 4), consumer group
-        const int L = q * 32 + lane;
-        const uint32_t t_lane = tm + ((uint32_t)(q * 32) << 16);
-        // One warp's share of a job done: order the TMEM reads before the barrier and release the columns.
-        auto release = [&](uint32_t b) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b);
-        };
-        auto publish = [&](uint32_t b) {                 // smem written by this warp -> visible to the MMA (async proxy)
+    if (warp < kL0Warps) {
+#if CNNACC_L0_DP4A
+        // =============== layer 0: dp4a on CUDA cores =============================================================
+        // One warp-iteration = one pooled row: 64 pooling windows x 16 out-channels, two adjacent windows per lane so
+        // the weight words (uniform registers) and the input words are fetched once for 384 dp4a.
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            const int slot = k & 1;
+            wait_or_flag(bar(kBarInFull0 + slot), (uint32_t)(k >> 1) & 1, kErrInputTimeout);
+            const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + (slot ? kOffIn1 : kOffIn0));
+#pragma unroll 1
+            for (int yp = warp; yp < 64; yp += kL0Warps) {
+                // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
+                // ones.  This unit writes row yp+1.
+                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                // windows xp = 2*lane and 2*lane+1 need pixel columns 4*lane-1 .. 4*lane+4 = slot bytes 4*lane+15 .. 4*lane+20
+                const uint32_t* rp = in_w + (2 * yp) * (kInPitch / 4) + lane + 3;
+                uint32_t A[4], B[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t w0 = rp[r * (kInPitch / 4)], w1 = rp[r * (kInPitch / 4) + 1], w2 = rp[r * (kInPitch / 4) + 2];
+                    A[r] = __funnelshift_r(w0, w1, 24);
+                    B[r] = __funnelshift_r(w1, w2, 8);
+                }
+                uint32_t va[4], vb[4];
+#pragma unroll
+                for (int o4 = 0; o4 < 4; o4++) {
+                    int pa[4], pb[4];
+#pragma unroll
+                    for (int oo = 0; oo < 4; oo++) {
+                        const int o = o4 * 4 + oo;
+                        const uint32_t l0 = P.w0[o][0], l1 = P.w0[o][1], l2 = P.w0[o][2];
+                        const uint32_t h0 = P.w0[o][3], h1 = P.w0[o][4], h2 = P.w0[o][5];
+                        int a00 = dp4a_u8s8(A[0], l0, dp4a_u8s8(A[1], l1, dp4a_u8s8(A[2], l2, 0)));
+                        int a01 = dp4a_u8s8(A[0], h0, dp4a_u8s8(A[1], h1, dp4a_u8s8(A[2], h2, 0)));
+                        int a10 = dp4a_u8s8(A[1], l0, dp4a_u8s8(A[2], l1, dp4a_u8s8(A[3], l2, 0)));
+                        int a11 = dp4a_u8s8(A[1], h0, dp4a_u8s8(A[2], h1, dp4a_u8s8(A[3], h2, 0)));
+                        int b00 = dp4a_u8s8(B[0], l0, dp4a_u8s8(B[1], l1, dp4a_u8s8(B[2], l2, 0)));
+                        int b01 = dp4a_u8s8(B[0], h0, dp4a_u8s8(B[1], h1, dp4a_u8s8(B[2], h2, 0)));
+                        int b10 = dp4a_u8s8(B[1], l0, dp4a_u8s8(B[2], l1, dp4a_u8s8(B[3], l2, 0)));
+                        int b11 = dp4a_u8s8(B[1], h0, dp4a_u8s8(B[2], h1, dp4a_u8s8(B[3], h2, 0)));
+                        pa[oo] = max4(a00, a01, a10, a11);
+                        pb[oo] = max4(b00, b01, b10, b11);
+                    }
+                    va[o4] = act_pack4(pa[0], pa[1], pa[2], pa[3], P.shift0);
+                    vb[o4] = act_pack4(pb[0], pb[1], pb[2], pb[3], P.shift0);
+                }
+                // window 2*lane -> halo column 2*lane+1 (odd plane, index lane); window 2*lane+1 -> column 2*lane+2 (even
+                // plane, index lane+1): both 16-byte stores are contiguous across the warp
+                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P;
+                *reinterpret_cast<uint4*>(row + kA1Q + lane * 16) = make_uint4(va[0], va[1], va[2], va[3]);
+                *reinterpret_cast<uint4*>(row + (lane + 1) * 16) = make_uint4(vb[0], vb[1], vb[2], vb[3]);
+                if (P.dump_l0) {                         // debug / register-protocol path: BRAM channels 0-15
+                    uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        d[c * 4096] = (uint8_t)(va[c >> 2] >> (8 * (c & 3)));
+                        d[c * 4096 + 1] = (uint8_t)(vb[c >> 2] >> (8 * (c & 3)));
+                    }
+                }
+                if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
+                    fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarA1TopReady));
+                }
+            }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(b);
-        };
-        // One "full" barrier per consumer group: the MMA warp commits each job to the group that owns it, so a group
-        // sees every phase of its barrier in order (a parity wait is only meaningful for the phase right after the
-        // last one the waiter has seen -- a barrier shared by groups that take turns would alias).
-        uint32_t my_jobs = 0;
-        auto wait_job = [&]() {
-            wait_or_flag(bar(kBarFullG0 + g), my_jobs & 1, kErrMmaTimeout);
-            my_jobs++;
-        };
-        // ---- layer-0 tile t (pooled rows 4t..4t+3) from quarter qi; TMEM lane = (row % 4, column group) ----
-        auto drain_l0 = [&](int img, int t, int qi) {
-            wait_job();
-            tc_fence_after();
-            const uint32_t taddr = t_lane + qi * 128;
-            const int yp = 4 * t + q;
-            uint8_t* rowp = smem + kOffA1 + (yp + 1) * kA1P;
-            uint2 w[4];
-#pragma unroll
-            for (int half = 0; half < 2; half++) {       // two column quarters per pass (64 live accumulators)
-                int va[16], vb[16], vc[16], vd[16];
-                tmem_ld16(taddr + half * 64, va); tmem_ld16(taddr + half * 64 + 16, vb);
-                tmem_ld16(taddr + half * 64 + 32, vc); tmem_ld16(taddr + half * 64 + 48, vd);
-                tmem_ld_wait();
-                if (half == 1) release(bar(kBarEmptyQ0 + qi));
-                w[2 * half] = pool_act_8ch(va, vb, P.shift0);
-                w[2 * half + 1] = pool_act_8ch(vc, vd, P.shift0);
-            }
-            // column quarter cq = 2*w2 + och: window 2*lane + w2, channels 8*och..+7 -> one 16-byte vector per window
-            // window 2*lane -> halo column odd (plane 1, index lane); window 2*lane+1 -> even plane, index lane+1
-            *reinterpret_cast<uint4*>(rowp + kA1Q + lane * 16) = make_uint4(w[0].x, w[0].y, w[1].x, w[1].y);
-            *reinterpret_cast<uint4*>(rowp + (lane + 1) * 16) = make_uint4(w[2].x, w[2].y, w[3].x, w[3].y);
-            if (P.dump_l0) {                             // debug / register-protocol path: BRAM channels 0-15
-                uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
-#pragma unroll
-                for (int c = 0; c < 16; c++) {
-                    const uint2 e0 = w[c >> 3], e1 = w[2 + (c >> 3)];
-                    d[c * 4096] = (uint8_t)(((c & 4) ? e0.y : e0.x) >> (8 * (c & 3)));
-                    d[c * 4096 + 1] = (uint8_t)(((c & 4) ? e1.y : e1.x) >> (8 * (c & 3)));
-                }
-            }
-        };
-        // ---- layer-1 tile t (128 pooling windows) from quarter qi; columns = (oc/8)*32 + member*8 + oc%8 ----
-        auto drain_l1 = [&](int img, int t, int qi) {
-            wait_job();
-            tc_fence_after();
-            const uint32_t taddr = t_lane + qi * 128;
-            const int i = (t >> 2) * 16 + (L >> 3), jj = (t & 3) * 8 + (L & 7);
-            uint8_t* px = smem + kOffA2 + (i + 1) * kA2P + ((jj + 1) & 1) * kA2Q + ((jj + 1) >> 1) * 16;
-            uint2 w[4];
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                int va[16], vb[16], vc[16], vd[16];
-                tmem_ld16(taddr + half * 64, va); tmem_ld16(taddr + half * 64 + 16, vb);
-                tmem_ld16(taddr + half * 64 + 32, vc); tmem_ld16(taddr + half * 64 + 48, vd);
-                tmem_ld_wait();
-                if (half == 1) release(bar(kBarEmptyQ0 + qi));
-                w[2 * half] = pool_act_8ch(va, vb, P.shift1);
-                w[2 * half + 1] = pool_act_8ch(vc, vd, P.shift1);
-            }
-            *reinterpret_cast<uint4*>(px) = make_uint4(w[0].x, w[0].y, w[1].x, w[1].y);              // channels 0-15
-            *reinterpret_cast<uint4*>(px + kA2C) = make_uint4(w[2].x, w[2].y, w[3].x, w[3].y);       // channels 16-31
-            if (P.dump_l1) {                             // BRAM channels 16-47
-                uint8_t* d = P.dump_l1 + (size_t)img * 32768 + i * 32 + jj;
-#pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const uint2 e = w[c >> 3];
-                    d[c * 1024] = (uint8_t)(((c & 4) ? e.y : e.x) >> (8 * (c & 3)));
-                }
-            }
-        };
-        // ---- layer-2 block s, channel half hh (32 oc) from region A -> staging (CHW) ----
-        auto drain_l2 = [&](int s, int hh, int col0, bool wait_stage, uint32_t stage_par) {
-            wait_job();
-            tc_fence_after();
-            if (wait_stage) wait_or_flag(bar(kBarStageFree), stage_par, kErrSlotTimeout);   // previous image's store has read staging
-            const int i = L >> 3, j = s * 8 + (L & 7);
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int cg = 2 * hh + cc;              // group of 16 output channels
-                const uint32_t taddr = t_lane + col0 + cg * 16;
-                int m[16];
-                {
-                    int v0[16], v1[16];
-                    tmem_ld16(taddr, v0);
-                    tmem_ld16(taddr + 64, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; c++) m[c] = max(v0[c], v1[c]);
-                    tmem_ld16(taddr + 128, v0);
-                    tmem_ld16(taddr + 192, v1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; c++) m[c] = max(m[c], max(v0[c], v1[c]));
-                }
-                if (cc == 1) release(bar(col0 ? kBarEmptyB : kBarEmptyA));
-                uint8_t* o = smem + kOffStage + (cg * 16) * 256 + i * 16 + j;
-#pragma unroll
-                for (int c = 0; c < 16; c++) o[c * 256] = (uint8_t)act_u8(m[c], P.shift2);
-            }
-            publish(bar(kBarStageFull));
-        };
-
-        const int hh = g & 1;                            // quarter within the pair / channel half of a layer-2 block
-        if (g < 2) {
-            // ---- groups 0,1 (fed by issuer A): layer-1 tiles t = hh, hh+2, hh+4, hh+6 on quarter hh, then block 0 ----
-            for (int k = 0; k < n_local; k++) {
-                const int img = (int)blockIdx.x + k * (int)gridDim.x;
-                if (k > 0) wait_or_flag(bar(kBarL2DoneB), (uint32_t)(k - 1) & 1, kErrAct2Timeout);   // act2 no longer read by block 1 of image k-1
-#pragma unroll 1
-                for (int m = 0; m < 4; m++) drain_l1(img, hh + 2 * m, hh);
-                publish(bar(kBarA2Ready));
-                drain_l2(0, hh, 0, k > 0, (uint32_t)(k - 1) & 1);
-            }
-        } else {
-            // ---- groups 2,3 (fed by issuer B): layer-0 tiles t = hh, hh+2, ... on quarter 2+hh; block 1 of the previous
-            // image comes after this group's 5th tile (that is where issuer B commits it) ----
-            for (int j = 0; j <= n_local; j++) {
-                const int img = (int)blockIdx.x + j * (int)gridDim.x;
-                if (j < n_local) {
-#pragma unroll 1
-                    for (int m = 0; m < 8; m++) {
-                        const int t = hh + 2 * m;
-                        // act1 rows this tile writes (4t+1 .. 4t+4) may still be read by layer 1 of image j-1:
-                        // rows 0-33 by its top tiles, rows 32-65 by its bottom tiles
-                        if (j > 0 && m == 0) wait_or_flag(bar(kBarL1TopDone), (uint32_t)(j - 1) & 1, kErrAct1Timeout);
-                        if (j > 0 && t >= 7 && t - 2 < 7) wait_or_flag(bar(kBarL1Done), (uint32_t)(j - 1) & 1, kErrAct1Timeout);
-                        if (m == 5 && j > 0) drain_l2(1, hh, 256, j > 1, (uint32_t)(j - 2) & 1);
-                        drain_l0(img, t, 2 + hh);
-                        if (t <= 8 && t + 2 > 8) publish(bar(kBarA1TopReady));
-                    }
-                    publish(bar(kBarA1BotReady));
-                } else {
-                    drain_l2(1, hh, 256, j > 1, (uint32_t)(j - 2) & 1);
-                }
-            }
+            if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
         }
-    } else if (warp == kWarpMmaA || warp == kWarpMmaB) {
-        // =============== MMA issuers: the whole warp walks its schedule, one elected lane issues ==================
-        wait_or_flag(bar(kBarW), 0, kErrWeightTimeout);
-        constexpr uint32_t idesc128 = umma_idesc_i8(128), idesc64 = umma_idesc_i8(64);
-        // wait until job n-1 on a quarter / region has been drained: completion #(n-1), trivially true for n = 0
-        auto wait_drained = [&](uint32_t b, uint32_t n) { wait_or_flag(bar(b), (n & 1) ^ 1, kErrEmptyTimeout); };
-        // layer-2 block s into the 256 columns at col0: 4 parities x 9 taps, N = 64
-        auto issue_l2 = [&](int s, uint32_t col0) {
-            const uint64_t a0 = umma_desc(s_base + kOffA2 + (s * 8) * 16, kA2C, 2 * kA2P);
-            const uint64_t b0 = umma_desc(s_base + kOffB2, 1024, 128);
+#else
+        // =============== layer 0: warp-level int8 MMA (mma.sync m16n8k16), accumulators in registers ===============
+        // A row = one 2x2 pooling window, K = its 4x4 input patch (k = 4*patch row + patch column), N = 8 columns =
+        // (4 out-channels) x (horizontal window member px); 8 column blocks = (vertical member py) x (oc%4).  Lane
+        // (g,t) ends up with all four members of window g (and g+8) for out-channels 4t..4t+3: the pool is
+        // thread-local and the result is one packed word of the 16-channel act1 vector.  One warp-iteration = one
+        // pooled row = 4 fragments of 16 windows (even windows in rows 0-7, odd ones in rows 8-15 so that both
+        // 128-byte stores of a fragment are contiguous in their parity plane).
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t bfr[8];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const int a = p >> 1, b = p & 1;
+        for (int blk = 0; blk < 8; blk++) bfr[blk] = P.w0f[blk][lane];
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            const int slot = k & 1;
+            wait_or_flag(bar(kBarInFull0 + slot), (uint32_t)(k >> 1) & 1, kErrInputTimeout);
+            const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + (slot ? kOffIn1 : kOffIn0));
+#pragma unroll 1
+            for (int yp = warp; yp < 64; yp += kL0Warps) {
+                // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
+                // ones.  This unit writes row yp+1.
+                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                // patch row t of windows 2g+16f (a0) and 2g+16f+1 (a1): image row 2yp-1+t, columns 4g+32f-1 .. +4
+                const uint32_t* rp = in_w + (2 * yp + t) * (kInPitch / 4) + g + 3;
+                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P + g * 16 + t * 4;
 #pragma unroll
-                for (int t = 0; t < 9; t++) {
-                    const int dy = t / 3, dx = t % 3;
-                    const int aoff = (a + dy) * kA2P + ((b + dx) & 1) * kA2Q + ((b + dx) >> 1) * 16;
-                    umma_i8(tm + col0 + p * 64, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)((t * 2048) >> 4), idesc64, t > 0);
+                for (int f = 0; f < 4; f++) {
+                    const uint32_t w0 = rp[8 * f], w1 = rp[8 * f + 1], w2 = rp[8 * f + 2];
+                    const uint32_t a0 = __funnelshift_r(w0, w1, 24), a1 = __funnelshift_r(w1, w2, 8);
+                    int c[8][4];
+#pragma unroll
+                    for (int blk = 0; blk < 8; blk++) {
+                        c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0;
+                        imma_16816(c[blk], a0, a1, bfr[blk]);
+                    }
+                    int pe[4], po[4];
+#pragma unroll
+                    for (int ol = 0; ol < 4; ol++) {
+                        pe[ol] = max4(c[ol][0], c[ol][1], c[4 + ol][0], c[4 + ol][1]);
+                        po[ol] = max4(c[ol][2], c[ol][3], c[4 + ol][2], c[4 + ol][3]);
+                    }
+                    const uint32_t we = act_pack4(pe[0], pe[1], pe[2], pe[3], P.shift0);
+                    const uint32_t wo = act_pack4(po[0], po[1], po[2], po[3], P.shift0);
+                    // window 2g+16f -> halo column odd (plane 1, index g+8f); window +1 -> even plane, index g+8f+1
+                    *reinterpret_cast<uint32_t*>(row + kA1Q + f * 128) = we;
+                    *reinterpret_cast<uint32_t*>(row + 16 + f * 128) = wo;
+                    if (P.dump_l0) {                     // debug / register-protocol path: BRAM channels 0-15
+                        uint8_t* d = P.dump_l0 + (size_t)img * 65536 + (size_t)(4 * t) * 4096 + yp * 64 + 2 * g + 16 * f;
+#pragma unroll
+                        for (int ol = 0; ol < 4; ol++) {
+                            d[ol * 4096] = (uint8_t)(we >> (8 * ol));
+                            d[ol * 4096 + 1] = (uint8_t)(wo >> (8 * ol));
+                        }
+                    }
+                }
+                if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
+                    fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarA1TopReady));
                 }
             }
-        };
-        if (warp == kWarpMmaA) {
-            // ---- issuer A: per image 8 layer-1 tiles (tile t -> quarter t%2, group t%2), then layer-2 block 0 in region A ----
-            uint32_t nq0 = 0, nq1 = 0, nA = 0;           // jobs issued so far on Q0 / Q1 / region A
-            for (int k = 0; k < n_local; k++) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
+        }
+#endif
+    } else if (warp < kWarpMma) {
+        // =============== epilogue warps ==========================================================================
+        const int e = warp - kL0Warps;
+        const int q = e & 3;                             // TMEM lane quarter (== warp % 4)
+        constexpr int kGStep = kEpiWarps / 4;            // 8 warps: each takes one channel half; 4 warps: both
+        const int g0 = e >> 2;
+        const int L = q * 32 + lane;
+        const uint32_t t_lane = tm + ((uint32_t)(q * 32) << 16);
+        uint32_t uses[2] = {0, 0};                       // completed uses of each TMEM half (same sequence as the MMA warp)
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            // ---- layer 1: 8 tiles of 128 pooling windows; TMEM -> pool -> shift/ReLU/saturate -> act2 (smem) ----
 #pragma unroll 1
-                for (int t = 0; t < 8; t++) {
-                    const int qi = t & 1;
-                    TRACE(0, 10 + t);
-                    if (t == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
-                    if (t == 4) wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
-                    TRACE(0, 20 + t);
-                    wait_drained(kBarEmptyQ0 + qi, qi ? nq1 : nq0);
-                    if (t < 2) wait_drained(kBarEmptyA, nA);     // the quarter was last used by block 0 of image k-1
-                    TRACE(0, 30 + t);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        // 8 Toeplitz K-slabs, N = 128
-                        const uint64_t a0 = umma_desc(s_base + kOffA1 + (32 * (t >> 2)) * kA1P + (8 * (t & 3)) * 16, kA1Q, 2 * kA1P);
-                        const uint64_t b0 = umma_desc(s_base + kOffB1, 2048, 128);
+            for (int t = 0; t < 8; t++) {
+                const int h = t & 1, i0 = (t >> 2) * 16, j0 = (t & 3) * 8;
+                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
+                uses[h]++;
+                tc_fence_after();
+                const int i = i0 + (L >> 3), j = j0 + (L & 7);
 #pragma unroll
-                        for (int sl = 0; sl < 8; sl++) {
-                            const int r = sl >> 1, sx = sl & 1;
-                            umma_i8(tm + qi * 128, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), b0 + (uint64_t)((sl * kB1Slab) >> 4), idesc128, sl > 0);
-                        }
-                        umma_commit(bar(kBarFullG0 + qi));
-                        if (t == 3) umma_commit(bar(kBarL1TopDone));
-                        if (t == 7) umma_commit(bar(kBarL1Done));
+                for (int g = g0; g < 2; g += kGStep) {   // channel half: 16 of the 32 output channels
+                    const uint32_t taddr = t_lane + h * 256 + g * 16;
+                    int mx[16];
+                    {
+                        int v0[16], v1[16];
+                        tmem_ld16(taddr, v0);
+                        tmem_ld16(taddr + 32, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; c++) mx[c] = max(v0[c], v1[c]);
+                        tmem_ld16(taddr + 64, v0);
+                        tmem_ld16(taddr + 96, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; c++) mx[c] = max(mx[c], max(v0[c], v1[c]));
                     }
-                    __syncwarp();
-                    if (qi) nq1++; else nq0++;
+                    if (g + kGStep >= 2) {               // last read of this TMEM half by this warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
+                    }
+                    uint4 w;
+                    w.x = act_pack4(mx[0], mx[1], mx[2], mx[3], P.shift1);
+                    w.y = act_pack4(mx[4], mx[5], mx[6], mx[7], P.shift1);
+                    w.z = act_pack4(mx[8], mx[9], mx[10], mx[11], P.shift1);
+                    w.w = act_pack4(mx[12], mx[13], mx[14], mx[15], P.shift1);
+                    *reinterpret_cast<uint4*>(smem + kOffA2 + g * kA2C + (i + 1) * kA2P + ((j + 1) & 1) * kA2Q + ((j + 1) >> 1) * 16) = w;
+                    if (P.dump_l1) {                     // BRAM channels 16-47
+                        uint8_t* d = P.dump_l1 + (size_t)img * 32768 + (size_t)(g * 16) * 1024 + i * 32 + j;
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int c = 0; c < 16; c++) d[c * 1024] = (uint8_t)(ww[c >> 2] >> (8 * (c & 3)));
+                    }
                 }
-                TRACE(0, 40);
-                wait_or_flag(bar(kBarA2Ready), (uint32_t)k & 1, kErrAct2Timeout);
-                TRACE(0, 41);
-                wait_drained(kBarEmptyQ0, nq0); wait_drained(kBarEmptyQ1, nq1); wait_drained(kBarEmptyA, nA);
-                TRACE(0, 42);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarA2Ready));
+
+            // ---- layer 2: 2 blocks of 128 pooling windows x 4 parities; -> staging (CHW) -> one 16 KiB TMA store ----
+            if (k > 0) {                                 // the previous image's store must have finished reading staging
+                if (e == 0 && lane == 0) bulk_store_wait_read();
+                epi_bar_sync();
+            }
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) {
+                const int h = s, j0 = s * 8;
+                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
+                uses[h]++;
+                tc_fence_after();
+                const int i = L >> 3, j = j0 + (L & 7);
+#pragma unroll
+                for (int c4 = 0; c4 < 4 / kGStep; c4++) {
+                    const int cg = (kGStep == 2) ? 2 * g0 + c4 : c4;     // group of 16 output channels
+                    const bool last_cg = (c4 == 4 / kGStep - 1);
+                    const uint32_t taddr = t_lane + h * 256 + cg * 16;
+                    int m[16];
+                    {
+                        int v0[16], v1[16];
+                        tmem_ld16(taddr, v0);
+                        tmem_ld16(taddr + 64, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; c++) m[c] = max(v0[c], v1[c]);
+                        tmem_ld16(taddr + 128, v0);
+                        tmem_ld16(taddr + 192, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 16; c++) m[c] = max(m[c], max(v0[c], v1[c]));
+                    }
+                    if (last_cg) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
+                    }
+                    uint8_t* o = smem + kOffStage + (cg * 16) * 256 + i * 16 + j;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) o[c * 256] = (uint8_t)act_u8(m[c], P.shift2);
+                }
+            }
+            fence_async_smem();
+            epi_bar_sync();
+            if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+        }
+        if (e == 0 && lane == 0) bulk_store_wait_all();
+    } else if (warp == kWarpMma) {
+        // =============== MMA issue: the whole warp walks the schedule, one elected lane issues ====================
+        wait_or_flag(bar(kBarW), 0, kErrWeightTimeout);
+        uint32_t uses[2] = {0, 0};
+        constexpr uint32_t idesc1 = umma_idesc_i8(128), idesc2 = umma_idesc_i8(64);
+        for (int k = 0; k < n_local; k++) {
+            // ---- layer 1: 8 tiles (2 row halves x 4 column blocks) x 8 K-slabs, N = 128 ----
+#pragma unroll 1
+            for (int t = 0; t < 8; t++) {
+                const int h = t & 1, ty = t >> 2, tx = t & 3;
+                if (t == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
+                if (t == 4) wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
+                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
+                uses[h]++;
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_l2(0, 0);
-                    umma_commit(bar(kBarFullG0)); umma_commit(bar(kBarFullG1));
+                    const uint32_t d = tm + h * 256;
+                    const uint64_t a0 = umma_desc(s_base + kOffA1 + (32 * ty) * kA1P + (8 * tx) * 16, kA1Q, 2 * kA1P);
+                    const uint64_t b0 = umma_desc(s_base + kOffB1, 2048, 128);
+#pragma unroll
+                    for (int sl = 0; sl < 8; sl++) {
+                        const int r = sl >> 1, sx = sl & 1;
+                        umma_i8(d, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), b0 + (uint64_t)((sl * kB1Slab) >> 4), idesc1, sl > 0);
+                    }
+                    umma_commit(bar(kBarTmFull0 + h));
+                    if (t == 3) umma_commit(bar(kBarA1TopFree));
+                    if (t == 7) umma_commit(bar(kBarA1BotFree));
                 }
                 __syncwarp();
-                TRACE(0, 43);
-                nA++;
             }
-        } else {
-            // ---- issuer B: per image 8 layer-0 tile PAIRS (tile 2c -> Q2 / group 2, tile 2c+1 -> Q3 / group 3), ONE MMA
-            // per tile (K = 32 is the whole patch, N = 128); layer-2 block 1 of the previous image goes into region B
-            // after pair 4 (by then act2 of that image is complete and layer 1 of this image has what it needs to start) ----
-            uint32_t nq2 = 0, nq3 = 0, nB = 0;
-            for (int j = 0; j <= n_local; j++) {
-                if (j < n_local) wait_or_flag(bar(kBarZReady), (uint32_t)j & 1, kErrZTimeout);
+            // ---- layer 2: 2 blocks x 4 parities x 9 taps, N = 64 ----
+            wait_or_flag(bar(kBarA2Ready), (uint32_t)k & 1, kErrAct2Timeout);
 #pragma unroll 1
-                for (int c = 0; c < 8; c++) {
-                    if (j < n_local) {
-                        TRACE(1, 50 + c);
-                        wait_drained(kBarEmptyQ2, nq2); wait_drained(kBarEmptyQ3, nq3);
-                        if (c == 0 || c == 5) wait_drained(kBarEmptyB, nB);       // region B was last used by a layer-2 block
-                        TRACE(1, 60 + c);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            // rows m = 32*(pooled row % 4) + column group: 8-row groups are 128 B apart, K half 1 is the next Z row
-                            const uint64_t a0 = umma_desc(s_base + kOffZ + (8 * c) * kZPitch, kZPitch, 128);
-                            const uint64_t b0 = umma_desc(s_base + kOffB0, 2048, 128);
-                            umma_i8(tm + 256, a0, b0, idesc128, 0);
-                            umma_commit(bar(kBarFullG2));
-                            umma_i8(tm + 384, a0 + (uint64_t)((4 * kZPitch) >> 4), b0, idesc128, 0);
-                            umma_commit(bar(kBarFullG3));
-                            if (c == 7) umma_commit(bar(kBarZFree));
+            for (int s = 0; s < 2; s++) {
+                const int h = s, j0 = s * 8;
+                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
+                uses[h]++;
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a0 = umma_desc(s_base + kOffA2 + j0 * 16, kA2C, 2 * kA2P);
+                    const uint64_t b0 = umma_desc(s_base + kOffB2, 1024, 128);
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const int a = p >> 1, b = p & 1;
+                        const uint32_t d = tm + h * 256 + p * 64;
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            const int dy = t / 3, dx = t % 3;
+                            const int aoff = (a + dy) * kA2P + ((b + dx) & 1) * kA2Q + ((b + dx) >> 1) * 16;
+                            umma_i8(d, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)((t * 2048) >> 4), idesc2, t > 0);
                         }
-                        __syncwarp();
-                        nq2++; nq3++;
                     }
-                    if (j > 0 && (c == 4 || (j == n_local && c == 0))) {
-                        // block 1 of image j-1
-                        TRACE(1, 70);
-                        wait_or_flag(bar(kBarA2Ready), (uint32_t)(j - 1) & 1, kErrAct2Timeout);
-                        TRACE(1, 71);
-                        wait_drained(kBarEmptyQ2, nq2); wait_drained(kBarEmptyQ3, nq3); wait_drained(kBarEmptyB, nB);
-                        TRACE(1, 72);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_l2(1, 256);
-                            umma_commit(bar(kBarFullG2)); umma_commit(bar(kBarFullG3));
-                            umma_commit(bar(kBarL2DoneB));
-                        }
-                        __syncwarp();
-                        TRACE(1, 73);
-                        nB++;
-                        if (j == n_local) break;
-                    }
+                    umma_commit(bar(kBarTmFull0 + h));
                 }
+                __syncwarp();
             }
-        }
-    } else if (warp == kWarpTma) {
-        // =============== TMA loads: weights once, then one image ahead of the Z builders ===========================
-        if (elect_one()) {
-            mbar_expect_tx(bar(kBarW), kB0Bytes + kB1Bytes + kB2Bytes);
-            bulk_load(s_base + kOffB0, P.b012, kB0Bytes + kB1Bytes + kB2Bytes, bar(kBarW));
-        }
-        __syncwarp();
-        for (int k = 0; k < n_local; k++) {
-            if (k >= 1) wait_or_flag(bar(kBarInFree), (uint32_t)(k - 1) & 1, kErrSlotTimeout);
-            if (elect_one()) {
-                mbar_expect_tx(bar(kBarInFull), kInBytes);
-                tma_load_image(s_base + kOffIn, &in_map, bar(kBarInFull), (int)blockIdx.x + k * (int)gridDim.x);
-            }
-            __syncwarp();
-        }
-    } else if (warp < kWarpStore) {
-        // =============== Z builders: image -> layer-0 A operand ===================================================
-        // Z[j][xg] (16 B) = image rows 2j-1 and 2j, columns 4*xg-1 .. 4*xg+6 (8 B each); out-of-image bytes are 0.
-        const int zw = warp - kWarpZ;
-        const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + kOffIn);
-        for (int k = 0; k < n_local; k++) {
-            wait_or_flag(bar(kBarInFull), (uint32_t)k & 1, kErrInputTimeout);
-            if (k >= 1) wait_or_flag(bar(kBarZFree), (uint32_t)(k - 1) & 1, kErrZTimeout);
-#pragma unroll 1
-            for (int j = zw; j < 65; j += kZWarps) {
-                const uint32_t* ra = in_w + (2 * j) * 32 + lane;         // slot row 2j = image row 2j-1
-                const uint32_t* rb = ra + 32;
-                const uint32_t a0 = ra[0], b0 = rb[0];
-                const uint32_t am = lane ? ra[-1] : 0u, bm = lane ? rb[-1] : 0u;
-                const uint32_t ap = lane < 31 ? ra[1] : 0u, bp = lane < 31 ? rb[1] : 0u;
-                uint4 z;
-                z.x = __funnelshift_r(am, a0, 24); z.y = __funnelshift_r(a0, ap, 24);
-                z.z = __funnelshift_r(bm, b0, 24); z.w = __funnelshift_r(b0, bp, 24);
-                *reinterpret_cast<uint4*>(smem + kOffZ + j * kZPitch + lane * 16) = z;
-            }
-            fence_async_smem();                          // generic-proxy writes -> visible to the MMA (async proxy)
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(bar(kBarZReady)); mbar_arrive(bar(kBarInFree)); }
         }
     } else {
-        // =============== feature store: one 16 KiB bulk copy per image ============================================
+        // =============== TMA loads: weights once, then every image two ahead of its consumer ======================
+        if (elect_one()) {
+            mbar_expect_tx(bar(kBarW), kB1Bytes + kB2Bytes);
+            bulk_load(s_base + kOffB1, P.b1, kB1Bytes, bar(kBarW));
+            bulk_load(s_base + kOffB2, P.b2, kB2Bytes, bar(kBarW));
+        }
+        __syncwarp();
         for (int k = 0; k < n_local; k++) {
-            wait_or_flag(bar(kBarStageFull), (uint32_t)k & 1, kErrSlotTimeout);
-            if (lane == 0) {
-                bulk_store(P.out + (size_t)((int)blockIdx.x + k * (int)gridDim.x) * 16384, s_base + kOffStage, kStageBytes);
-                bulk_store_wait_read();
-                mbar_arrive(bar(kBarStageFree));
+            const int slot = k & 1;
+            if (k >= 2) wait_or_flag(bar(kBarInFree0 + slot), (uint32_t)((k >> 1) - 1) & 1, kErrSlotTimeout);
+            if (elect_one()) {
+                mbar_expect_tx(bar(kBarInFull0 + slot), kInBytes);
+                tma_load_image(s_base + (slot ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + slot), (int)blockIdx.x + k * (int)gridDim.x);
             }
             __syncwarp();
         }
-        if (lane == 0) bulk_store_wait_all();
-        __syncwarp();
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------
-#ifdef CNNACC_TRACE
-    if (blockIdx.x == 0 && lane == 0 && (warp == kWarpMmaA || warp == kWarpMmaB)) trace_cnt[warp == kWarpMmaB ? 1 : 0] = trace_n;
-#endif
     tc_fence_before();
     __syncthreads();
-#ifdef CNNACC_TRACE
-    if (blockIdx.x == 0 && tid == 0) {
-        for (int r = 0; r < 2; r++)
-            for (int i = 0; i < trace_cnt[r]; i++)
-                printf("TRACE %d %d %u\n", r, (int)(trace_buf[r * kTraceMax + i] >> 24), trace_buf[r * kTraceMax + i] & 0xFFFFFFu);
-    }
-#endif
     if (tid == 0 && *s_err) {
         atomicOr(P.status, *s_err);
         *reinterpret_cast<volatile int*>(P.status_host) = *s_err;
         __threadfence_system();
     }
-    if (warp == kWarpMmaA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(kTmemCols) : "memory");
+    if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(kTmemCols) : "memory");
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
 struct FusedWeights {
     bool ready = false;
-    uint8_t* d_b012 = nullptr;    // layer 0 | 1 | 2 B operands, one bulk copy per CTA
+    uint32_t w0[16][6];
+    uint32_t w0f[8][32];
+    uint8_t* d_b1 = nullptr;
+    uint8_t* d_b2 = nullptr;
     int* d_status = nullptr;
     int* h_status = nullptr;      // mapped pinned mirror of the status word
     int* h_status_dev = nullptr;  // its device address
@@ -655,30 +615,38 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// Pure host permutation of weights.bin (parse_kernels, arm_cnn.c:43-59, done once) into the three B operands.
-// All are K-major no-swizzle: element (n, k) of a K=32 slab at (k/16)*LBO + (n/8)*128 + (n%8)*16 + k%16.
-inline void fused_pack_weights(const uint8_t* wbin, uint8_t* b0, uint8_t* b1, uint8_t* b2) {
-    std::memset(b0, 0, kB0Bytes);
+// Pure host permutation of weights.bin (parse_kernels, arm_cnn.c:43-59, done once) into the three operand layouts.
+inline void fused_pack_weights(const uint8_t* wbin, uint32_t w0[16][6], uint32_t w0f[8][32], uint8_t* b1, uint8_t* b2) {
+    // layer 0, mma.sync B fragments: lane (g,t) of block (py, ol) holds patch row r = t, columns c = 0..3 of
+    // output column n = g -> out-channel 4*(g>>1) + ol, horizontal member px = g&1:  w0[oc][r - py][c - px]
+    for (int blk = 0; blk < 8; blk++)
+        for (int lane = 0; lane < 32; lane++) {
+            const int py = blk >> 2, ol = blk & 3, g = lane >> 2, t = lane & 3, oc = 4 * (g >> 1) + ol, px = g & 1;
+            uint32_t word = 0;
+            for (int c = 0; c < 4; c++) {
+                const int dy = t - py, dx = c - px;
+                if (dy >= 0 && dy <= 2 && dx >= 0 && dx <= 2) word |= (uint32_t)weight_byte(wbin, 0, oc, 0, dy * 3 + dx) << (8 * c);
+            }
+            w0f[blk][lane] = word;
+        }
     std::memset(b1, 0, kB1Bytes);
     std::memset(b2, 0, kB2Bytes);
-    // layer 0: A row = two adjacent pooling windows, K byte k = 8*r + c = patch row r (0..3), patch column c (0..7).
-    // N row n = cq*32 + member*8 + oc8 with column quarter cq = 2*w2 + och (window w2 of the pair, channel half och),
-    // member = 2*py + px, oc = 8*och + oc8:   B[n][k] = w0[oc][r - py][c - (2*w2 + px)]  when both are in 0..2
-    for (int n = 0; n < 128; n++)
-        for (int kk = 0; kk < 32; kk++) {
-            const int cq = n >> 5, w2 = cq >> 1, och = cq & 1, mem = (n >> 3) & 3, py = mem >> 1, px = mem & 1, oc = 8 * och + (n & 7);
-            const int r = kk >> 3, c = kk & 7, dy = r - py, dx = c - (2 * w2 + px);
-            if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
-            b0[(kk >> 4) * 2048 + (n / 8) * 128 + (n % 8) * 16 + (kk & 15)] = weight_byte(wbin, 0, oc, 0, dy * 3 + dx);
+    for (int o = 0; o < 16; o++)
+        for (int dy = 0; dy < 3; dy++) {
+            uint32_t lo = (uint32_t)weight_byte(wbin, 0, o, 0, dy * 3) | (uint32_t)weight_byte(wbin, 0, o, 0, dy * 3 + 1) << 8 |
+                          (uint32_t)weight_byte(wbin, 0, o, 0, dy * 3 + 2) << 16;
+            w0[o][dy] = lo;
+            w0[o][3 + dy] = lo << 8;
         }
     // layer 1 (Toeplitz over a 2x2 pooling window): slab sl = (patch row r = sl/2, column pair sx = sl%2), K byte
-    // k = jx*16 + ic is patch pixel (r, 2*sx + jx) channel ic; N row n = (oc/8)*32 + member*8 + oc%8:
+    // k = jx*16 + ic is patch pixel (r, 2*sx + jx) channel ic, N row n = (py*2 + px)*32 + oc is window member (py,px):
     //   B[n][k] = w1[oc][ic][r - py][2*sx + jx - px]   when both tap indices are in 0..2, else 0
+    // stored K-major: sl*4096 + (k/16)*2048 + (n/8)*128 + (n%8)*16 + k%16
     for (int sl = 0; sl < 8; sl++)
         for (int n = 0; n < 128; n++)
             for (int kk = 0; kk < 32; kk++) {
-                const int r = sl >> 1, sx = sl & 1, mem = (n >> 3) & 3, py = mem >> 1, px = mem & 1, oc = (n >> 5) * 8 + (n & 7);
-                const int jx = kk >> 4, ic = kk & 15, dy = r - py, dx = 2 * sx + jx - px;
+                const int r = sl >> 1, sx = sl & 1, py = n >> 6, px = (n >> 5) & 1, oc = n & 31, jx = kk >> 4, ic = kk & 15;
+                const int dy = r - py, dx = 2 * sx + jx - px;
                 if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
                 b1[sl * kB1Slab + jx * 2048 + (n / 8) * 128 + (n % 8) * 16 + ic] = weight_byte(wbin, 1, oc, ic, dy * 3 + dx);
             }
@@ -692,10 +660,11 @@ inline void fused_pack_weights(const uint8_t* wbin, uint8_t* b0, uint8_t* b1, ui
 // Pack and upload.  Returns a cudaError_t as int.
 inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
     fw.ready = false;
-    std::vector<uint8_t> b(kB0Bytes + kB1Bytes + kB2Bytes);
-    fused_pack_weights(wbin, b.data(), b.data() + kB0Bytes, b.data() + kB0Bytes + kB1Bytes);
+    std::vector<uint8_t> b1(kB1Bytes), b2(kB2Bytes);
+    fused_pack_weights(wbin, fw.w0, fw.w0f, b1.data(), b2.data());
     cudaError_t e;
-    if (!fw.d_b012 && (e = cudaMalloc(&fw.d_b012, b.size())) != cudaSuccess) return (int)e;
+    if (!fw.d_b1 && (e = cudaMalloc(&fw.d_b1, kB1Bytes)) != cudaSuccess) return (int)e;
+    if (!fw.d_b2 && (e = cudaMalloc(&fw.d_b2, kB2Bytes)) != cudaSuccess) return (int)e;
     if (!fw.d_status) {
         if ((e = cudaMalloc(&fw.d_status, sizeof(int))) != cudaSuccess) return (int)e;
         if ((e = cudaMemset(fw.d_status, 0, sizeof(int))) != cudaSuccess) return (int)e;
@@ -703,7 +672,8 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
         *fw.h_status = 0;
         if ((e = cudaHostGetDevicePointer(&fw.h_status_dev, fw.h_status, 0)) != cudaSuccess) return (int)e;
     }
-    if ((e = cudaMemcpy(fw.d_b012, b.data(), b.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(fw.d_b1, b1.data(), kB1Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(fw.d_b2, b2.data(), kB2Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if (!fw.attr_set) {
         if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
         fw.attr_set = true;
@@ -714,9 +684,9 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
 }
 
 inline void fused_free(FusedWeights& fw) {
-    cudaFree(fw.d_b012); cudaFree(fw.d_status);
+    cudaFree(fw.d_b1); cudaFree(fw.d_b2); cudaFree(fw.d_status);
     if (fw.h_status) cudaFreeHost(fw.h_status);
-    fw.d_b012 = nullptr; fw.d_status = nullptr; fw.h_status = fw.h_status_dev = nullptr; fw.ready = false;
+    fw.d_b1 = fw.d_b2 = nullptr; fw.d_status = nullptr; fw.h_status = fw.h_status_dev = nullptr; fw.ready = false;
 }
 
 // Tensor map over n images [n][128][128] u8 at a device-accessible address (device memory or mapped pinned host memory).
@@ -724,7 +694,7 @@ inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map) 
     if (n <= 0 || n > 0x7fffffff || (reinterpret_cast<uintptr_t>(d_imgs) & 15) || !get_encode_tiled()) return (int)cudaErrorInvalidValue;
     const cuuint64_t gdim[3] = {128, 128, (cuuint64_t)n};
     const cuuint64_t gstride[2] = {128, 16384};
-    const cuuint32_t box[3] = {128, (cuuint32_t)kInRows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)kInPitch, (cuuint32_t)kInRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_imgs), gdim, gstride, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -736,9 +706,11 @@ inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map) 
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
                             const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
     FusedParams P;
+    std::memcpy(P.w0, fw.w0, sizeof(P.w0));
+    std::memcpy(P.w0f, fw.w0f, sizeof(P.w0f));
     P.shift0 = shifts[0]; P.shift1 = shifts[1]; P.shift2 = shifts[2];
     P.n_images = (int)n;
-    P.b012 = fw.d_b012;
+    P.b1 = fw.d_b1; P.b2 = fw.d_b2;
     P.out = d_feats; P.dump_l0 = dump_l0; P.dump_l1 = dump_l1;
     P.status = fw.d_status; P.status_host = fw.h_status_dev;
     const int grid = (int)std::min<int64_t>(n, sm_count);

@@ -1,8 +1,7 @@
 """CPU re-derivation of the fused kernel's operand layouts (no GPU needed).
 
 The fused kernel (csrc/conv_fused.cuh) never materialises im2col: it points tcgen05 shared-memory descriptors
-(start address, LBO, SBO) into halo-padded activation maps (layers 1-2), into the Z re-layout of the image
-(layer 0) and into weights permuted by
+(start address, LBO, SBO) into halo-padded activation maps and into weights permuted by
 cnnacc_pack_weights_host.  This test replays exactly that addressing in numpy -- a K-major no-swizzle operand
 element (row, k) lives at  start + (row/8)*SBO + (k/16)*LBO + (row%8)*16 + k%16  -- builds the accumulators the
 MMAs would produce, applies the kernel's epilogue (pool raw s32, then shift/saturate) and checks every layer
@@ -29,12 +28,12 @@ B1_SLAB = 4096
 
 def pack(weights):
     lib = fc.load()
-    b0 = np.zeros(4096, np.uint8)
+    w0 = np.zeros(352, np.uint32)
     b1 = np.zeros(32768, np.uint8)
     b2 = np.zeros(18432, np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    assert lib.cnnacc_pack_weights_host(p(weights), weights.size, p(b0), p(b1), p(b2)) == 0
-    return b0, b1, b2
+    assert lib.cnnacc_pack_weights_host(p(weights), weights.size, p(w0), p(b1), p(b2)) == 0
+    return w0[:96].reshape(16, 6), w0[96:].reshape(8, 32), b1, b2
 
 
 def operand(buf, start, lbo, sbo, rows, signed):
@@ -50,33 +49,42 @@ def act(v, shift):
     return np.clip(v >> shift, 0, 255).astype(np.uint8)
 
 
-def build_z(img):
-    """The Z builders' re-layout: Z[j][xg] (16 B) = image rows 2j-1, 2j x columns 4xg-1 .. 4xg+6, zero outside."""
-    pad = np.zeros((131, 136), np.uint8)                       # rows -1..129, cols -1..134
-    pad[1:129, 1:129] = img
-    z = np.zeros(65 * 512, np.uint8)
-    for j in range(65):
-        for xg in range(32):
-            off = j * 512 + xg * 16
-            z[off:off + 8] = pad[2 * j, 4 * xg:4 * xg + 8]             # image row 2j-1
-            z[off + 8:off + 16] = pad[2 * j + 1, 4 * xg:4 * xg + 8]    # image row 2j
-    return z
-
-
-def layer0_umma(img, b0, shift):
-    """16 tiles, ONE K=32 MMA each: row m = (pooled row % 4, column group), N = quarter*32 + member*8 + oc8."""
-    z = build_z(img)
-    B = operand(b0, 0, 2048, 128, 128, signed=True)
+def layer0_dp4a(img, w0, shift):
+    """Layer 0 as the dp4a loop computes it: 4-byte row windows dotted with lo / hi weight words."""
+    pad = np.zeros((130, 160), np.int64)
+    pad[1:129, 16:144] = img
+    w = np.zeros((16, 6, 4), np.int64)
+    for b in range(4):
+        w[:, :, b] = ((w0 >> (8 * b)) & 0xFF).astype(np.uint8).view(np.int8).reshape(16, 6)
     out = np.zeros((16, 64, 64), np.uint8)
-    for t in range(16):
-        A = operand(z, 4 * t * 512, 512, 128, 128, signed=False)
-        D = A @ B.T                                                  # [128][128]
-        pooled = D.reshape(128, 4, 4, 8).max(axis=2)                 # [m][quarter][oc8]
-        m = np.arange(128)
-        yp, xg = 4 * t + (m >> 5), m & 31
-        for cq in range(4):
-            w2, och = cq >> 1, cq & 1
-            out[8 * och:8 * och + 8, yp, 2 * xg + w2] = act(pooled[:, cq, :], shift).T
+    yp, xp = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    cb = 2 * xp + 15
+    A = np.stack([np.stack([pad[2 * yp + r, cb + b] for b in range(4)], -1) for r in range(4)])   # [4][64][64][4]
+    for o in range(16):
+        a00 = sum((A[d] * w[o, d]).sum(-1) for d in range(3))
+        a01 = sum((A[d] * w[o, 3 + d]).sum(-1) for d in range(3))
+        a10 = sum((A[d + 1] * w[o, d]).sum(-1) for d in range(3))
+        a11 = sum((A[d + 1] * w[o, 3 + d]).sum(-1) for d in range(3))
+        out[o] = act(np.maximum(np.maximum(a00, a01), np.maximum(a10, a11)), shift)
+    return out
+
+
+def layer0_imma(img, w0f, shift):
+    """Layer 0 as the mma.sync fragments compute it: A row = a window's 4x4 patch (k = 4*row + col), B fragment word
+    of lane 4*n + r in block (py, ol) = patch row r of output column n -> (oc = 4*(n>>1) + ol, px = n&1)."""
+    pad = np.zeros((130, 160), np.int64)
+    pad[1:129, 16:144] = img
+    yp, xp = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    patch = np.stack([np.stack([pad[2 * yp + r, 2 * xp + 15 + c] for c in range(4)], -1) for r in range(4)], -2)   # [64][64][r][c]
+    B = np.zeros((8, 8, 4, 4), np.int64)                                  # [blk][n][r][c]
+    for c in range(4):
+        B[:, :, :, c] = ((w0f >> (8 * c)) & 0xFF).astype(np.uint8).view(np.int8).reshape(8, 8, 4)
+    D = np.einsum("yxrc,bnrc->yxbn", patch, B)                            # [64][64][blk][n]
+    out = np.zeros((16, 64, 64), np.uint8)
+    for n2 in range(4):
+        for ol in range(4):
+            members = [D[:, :, py * 4 + ol, 2 * n2 + px] for py in range(2) for px in range(2)]
+            out[4 * n2 + ol] = act(np.maximum.reduce(members), shift)
     return out
 
 
@@ -102,7 +110,7 @@ def layer1_umma(a1, b1, shift):
             A = operand(a1, a0 + r * A1P + sx * 16, A1Q, 2 * A1P, 128, signed=False)
             B = operand(b1, sl * B1_SLAB, 2048, 128, 128, signed=True)
             D += A @ B.T
-        pooled = D.reshape(128, 4, 4, 8).max(axis=2).reshape(128, 32)   # lane = window, columns = (oc/8)*32 + member*8 + oc%8
+        pooled = D.reshape(128, 4, 32).max(axis=1)                   # lane = window, columns = member*32 + oc
         L = np.arange(128)
         out[:, 16 * ty + (L >> 3), 8 * tx + (L & 7)] = act(pooled, shift).T
     return out
@@ -151,9 +159,10 @@ def test_packed_operands_reproduce_the_oracle(wkind, shifts):
     wt = inputs.make_weights(wkind, shipped)
     img = inputs.make_images(("rng", 42), 1)[0]
     want, want_l0, want_l1 = np_oracle.infer(img, np_oracle.unpack_weights(wt), shifts, return_all=True)
-    b0, b1, b2 = pack(wt)
-    l0 = layer0_umma(img, b0, shifts[0])
-    assert np.array_equal(l0, want_l0), "layer-0 Z layout / Toeplitz operand / descriptors"
+    w0, w0f, b1, b2 = pack(wt)
+    l0 = layer0_dp4a(img, w0, shifts[0])
+    assert np.array_equal(l0, want_l0), "layer-0 dp4a words"
+    assert np.array_equal(layer0_imma(img, w0f, shifts[0]), want_l0), "layer-0 mma.sync B fragments"
     l1 = layer1_umma(store_act1(l0), b1, shifts[1])
     assert np.array_equal(l1, want_l1), "layer-1 Toeplitz operand / descriptors"
     l2 = layer2_umma(store_act2(l1), b2, shifts[2])
@@ -163,6 +172,5 @@ def test_packed_operands_reproduce_the_oracle(wkind, shifts):
 def test_toeplitz_density():
     """56.25 % of the layer-1 B operand is structurally non-zero (36 of 64 (member, patch pixel) pairs)."""
     wt = np.full(23184, 1, np.uint8)
-    b0, b1, _ = pack(wt)
+    _, _, b1, _ = pack(wt)
     assert np.count_nonzero(b1) == 36 * 32 * 16
-    assert np.count_nonzero(b0) == 2 * 4 * 9 * 16                     # 2 windows x 4 members x 9 taps x 16 oc of 4096 slots
