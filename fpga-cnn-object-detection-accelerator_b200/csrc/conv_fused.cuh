@@ -70,8 +70,26 @@ constexpr int kOffStage = kOffB2 + kB2Bytes;          // 199680
 constexpr int kOffBar   = kOffStage + kStageBytes;    // 216064
 constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
 
-#ifndef CNNACC_L0_DP4A
-#define CNNACC_L0_DP4A 0      // 1 = layer 0 on the dp4a pipe (the first design; kept for the ablation in profiles/)
+// Optional schedule trace (tools only, -DCNNACC_TRACE): CTA 0 records clock() at pipeline events in shared memory and
+// prints them at exit (tools/trace_run.py).
+#ifdef CNNACC_TRACE
+#include <cstdio>
+constexpr int kTraceMax = 200, kTraceRoles = 4;
+#define TRACE(role, code)                                                                                          \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && lane == 0 && trace_n < kTraceMax) {                                                 \
+            trace_buf[(role) * kTraceMax + trace_n] = ((unsigned)(code) << 24) | ((unsigned)clock64() & 0xFFFFFFu);   \
+            trace_n++;                                                                                             \
+        }                                                                                                          \
+    } while (0)
+#define TRACE_END(role) do { if (blockIdx.x == 0 && lane == 0) trace_cnt[role] = trace_n; } while (0)
+#else
+#define TRACE(role, code) do { } while (0)
+#define TRACE_END(role) do { } while (0)
+#endif
+
+#ifndef CNNACC_L0_DP4A_WARPS
+#define CNNACC_L0_DP4A_WARPS 8     // layer-0 warps that use dp4a; the rest use mma.sync (0 and 16 = the single-pipe ablations)
 #endif
 #ifndef CNNACC_L0_WARPS
 #define CNNACC_L0_WARPS 16
@@ -79,6 +97,7 @@ constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
 #ifndef CNNACC_EPI_WARPS
 #define CNNACC_EPI_WARPS 4
 #endif
+constexpr int kL0Dp4aWarps = CNNACC_L0_DP4A_WARPS;
 constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
 static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
 constexpr int kWarpMma = kL0Warps + kEpiWarps, kWarpTma = kWarpMma + 1;
@@ -91,7 +110,7 @@ enum : uint32_t {
     kBarA1TopReady, kBarA1BotReady,                                 // layer 0 -> MMA  (act1 rows 0-33 / all rows written)
     kBarA1TopFree, kBarA1BotFree,                                   // MMA (tcgen05.commit) -> layer 0
     kBarTmFull0, kBarTmFull1, kBarTmEmpty0, kBarTmEmpty1,           // MMA -> epilogue ; epilogue -> MMA (TMEM halves)
-    kBarA2Ready,                                                    // epilogue -> MMA (act2 complete)
+    kBarA2ReadyA, kBarA2ReadyB,                                     // epilogue -> MMA: act2 written by tiles 0-6 (all block 0 needs) / by all 8
     kBarW,                                                          // weights landed
     kNumBars
 };
@@ -224,6 +243,12 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform in the compiler's eyes
     const int n_local = (P.n_images - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // images of this CTA
+#ifdef CNNACC_TRACE
+    __shared__ unsigned trace_buf[kTraceRoles * kTraceMax];
+    __shared__ int trace_cnt[kTraceRoles];
+    int trace_n = 0;
+    if (tid < kTraceRoles) trace_cnt[tid] = 0;
+#endif
 
     // ---- one-time setup ---------------------------------------------------------------------------------
     for (int i = tid; i < (kA1Alloc + kA2Bytes) / 16; i += kFusedThreads)                       // zero halos (and interiors)
@@ -235,7 +260,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         mbar_init(bar(kBarA1TopFree), 1); mbar_init(bar(kBarA1BotFree), 1);
         mbar_init(bar(kBarTmFull0), 1); mbar_init(bar(kBarTmFull1), 1);
         mbar_init(bar(kBarTmEmpty0), kEpiWarps); mbar_init(bar(kBarTmEmpty1), kEpiWarps);
-        mbar_init(bar(kBarA2Ready), kEpiWarps);
+        mbar_init(bar(kBarA2ReadyA), kEpiWarps); mbar_init(bar(kBarA2ReadyB), kEpiWarps);
         mbar_init(bar(kBarW), 1);
         *s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -257,84 +282,15 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     };
 
     if (warp < kL0Warps) {
-#if CNNACC_L0_DP4A
-        // =============== layer 0: dp4a on CUDA cores =============================================================
-        // One warp-iteration = one pooled row: 64 pooling windows x 16 out-channels, two adjacent windows per lane so
-        // the weight words (uniform registers) and the input words are fetched once for 384 dp4a.
-        for (int k = 0; k < n_local; k++) {
-            const int img = (int)blockIdx.x + k * (int)gridDim.x;
-            const int slot = k & 1;
-            wait_or_flag(bar(kBarInFull0 + slot), (uint32_t)(k >> 1) & 1, kErrInputTimeout);
-            const uint32_t* in_w = reinterpret_cast<const uint32_t*>(smem + (slot ? kOffIn1 : kOffIn0));
-#pragma unroll 1
-            for (int yp = warp; yp < 64; yp += kL0Warps) {
-                // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
-                // ones.  This unit writes row yp+1.
-                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                // windows xp = 2*lane and 2*lane+1 need pixel columns 4*lane-1 .. 4*lane+4 = slot bytes 4*lane+15 .. 4*lane+20
-                const uint32_t* rp = in_w + (2 * yp) * (kInPitch / 4) + lane + 3;
-                uint32_t A[4], B[4];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const uint32_t w0 = rp[r * (kInPitch / 4)], w1 = rp[r * (kInPitch / 4) + 1], w2 = rp[r * (kInPitch / 4) + 2];
-                    A[r] = __funnelshift_r(w0, w1, 24);
-                    B[r] = __funnelshift_r(w1, w2, 8);
-                }
-                uint32_t va[4], vb[4];
-#pragma unroll
-                for (int o4 = 0; o4 < 4; o4++) {
-                    int pa[4], pb[4];
-#pragma unroll
-                    for (int oo = 0; oo < 4; oo++) {
-                        const int o = o4 * 4 + oo;
-                        const uint32_t l0 = P.w0[o][0], l1 = P.w0[o][1], l2 = P.w0[o][2];
-                        const uint32_t h0 = P.w0[o][3], h1 = P.w0[o][4], h2 = P.w0[o][5];
-                        int a00 = dp4a_u8s8(A[0], l0, dp4a_u8s8(A[1], l1, dp4a_u8s8(A[2], l2, 0)));
-                        int a01 = dp4a_u8s8(A[0], h0, dp4a_u8s8(A[1], h1, dp4a_u8s8(A[2], h2, 0)));
-                        int a10 = dp4a_u8s8(A[1], l0, dp4a_u8s8(A[2], l1, dp4a_u8s8(A[3], l2, 0)));
-                        int a11 = dp4a_u8s8(A[1], h0, dp4a_u8s8(A[2], h1, dp4a_u8s8(A[3], h2, 0)));
-                        int b00 = dp4a_u8s8(B[0], l0, dp4a_u8s8(B[1], l1, dp4a_u8s8(B[2], l2, 0)));
-                        int b01 = dp4a_u8s8(B[0], h0, dp4a_u8s8(B[1], h1, dp4a_u8s8(B[2], h2, 0)));
-                        int b10 = dp4a_u8s8(B[1], l0, dp4a_u8s8(B[2], l1, dp4a_u8s8(B[3], l2, 0)));
-                        int b11 = dp4a_u8s8(B[1], h0, dp4a_u8s8(B[2], h1, dp4a_u8s8(B[3], h2, 0)));
-                        pa[oo] = max4(a00, a01, a10, a11);
-                        pb[oo] = max4(b00, b01, b10, b11);
-                    }
-                    va[o4] = act_pack4(pa[0], pa[1], pa[2], pa[3], P.shift0);
-                    vb[o4] = act_pack4(pb[0], pb[1], pb[2], pb[3], P.shift0);
-                }
-                // window 2*lane -> halo column 2*lane+1 (odd plane, index lane); window 2*lane+1 -> column 2*lane+2 (even
-                // plane, index lane+1): both 16-byte stores are contiguous across the warp
-                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P;
-                *reinterpret_cast<uint4*>(row + kA1Q + lane * 16) = make_uint4(va[0], va[1], va[2], va[3]);
-                *reinterpret_cast<uint4*>(row + (lane + 1) * 16) = make_uint4(vb[0], vb[1], vb[2], vb[3]);
-                if (P.dump_l0) {                         // debug / register-protocol path: BRAM channels 0-15
-                    uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
-#pragma unroll
-                    for (int c = 0; c < 16; c++) {
-                        d[c * 4096] = (uint8_t)(va[c >> 2] >> (8 * (c & 3)));
-                        d[c * 4096 + 1] = (uint8_t)(vb[c >> 2] >> (8 * (c & 3)));
-                    }
-                }
-                if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
-                    fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarA1TopReady));
-                }
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
-        }
-#else
-        // =============== layer 0: warp-level int8 MMA (mma.sync m16n8k16), accumulators in registers ===============
-        // A row = one 2x2 pooling window, K = its 4x4 input patch (k = 4*patch row + patch column), N = 8 columns =
-        // (4 out-channels) x (horizontal window member px); 8 column blocks = (vertical member py) x (oc%4).  Lane
-        // (g,t) ends up with all four members of window g (and g+8) for out-channels 4t..4t+3: the pool is
-        // thread-local and the result is one packed word of the 16-channel act1 vector.  One warp-iteration = one
-        // pooled row = 4 fragments of 16 windows (even windows in rows 0-7, odd ones in rows 8-15 so that both
-        // 128-byte stores of a fragment are contiguous in their parity plane).
+        // =============== layer 0 (1->16, K=9): two instruction mixes on two different pipes ========================
+        // One warp-iteration = one pooled row (64 pooling windows x 16 out-channels), 2x2 pool + shift/saturate in
+        // registers, 16-channel vectors stored straight into act1.  Warps 0..kL0Dp4aWarps-1 compute their rows with
+        // dp4a (IDP pipe: 64 lanes/clk/SM, 3 useful MACs per lane-op), the others with warp-level int8 MMA
+        // (mma.sync m16n8k16 on the tensor pipe: 2 clk/SM per instruction, shared with the tcgen05 MMAs of layers
+        // 1-2).  Neither pipe alone is fast enough (profiles/: dp4a-only 16.4 M img/s with the IDP pipe saturated,
+        // mma.sync-only 17.9 M with the tensor pipe saturated); split between them both have headroom.
+        const bool use_dp4a = warp < kL0Dp4aWarps;
+        // mma.sync operands: lane (g,t); B fragments stay in registers for the whole kernel
         const int g = lane >> 2, t = lane & 3;
         uint32_t bfr[8];
 #pragma unroll
@@ -350,39 +306,96 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 // ones.  This unit writes row yp+1.
                 if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
                 if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                // patch row t of windows 2g+16f (a0) and 2g+16f+1 (a1): image row 2yp-1+t, columns 4g+32f-1 .. +4
-                const uint32_t* rp = in_w + (2 * yp + t) * (kInPitch / 4) + g + 3;
-                uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P + g * 16 + t * 4;
+                if (warp == 0) TRACE(2, 1); else if (warp == kL0Warps - 1) TRACE(3, 1);
+                if (use_dp4a) {
+                    // ---- dp4a: two adjacent windows per lane (xp = 2*lane, 2*lane+1) so the weight words (uniform
+                    // registers) and the input words are fetched once for 384 dp4a.  Pixel columns 4*lane-1 .. 4*lane+4
+                    // = slot bytes 4*lane+15 .. 4*lane+20 ----
+                    const uint32_t* rp = in_w + (2 * yp) * (kInPitch / 4) + lane + 3;
+                    uint32_t A[4], B[4];
 #pragma unroll
-                for (int f = 0; f < 4; f++) {
-                    const uint32_t w0 = rp[8 * f], w1 = rp[8 * f + 1], w2 = rp[8 * f + 2];
-                    const uint32_t a0 = __funnelshift_r(w0, w1, 24), a1 = __funnelshift_r(w1, w2, 8);
-                    int c[8][4];
-#pragma unroll
-                    for (int blk = 0; blk < 8; blk++) {
-                        c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0;
-                        imma_16816(c[blk], a0, a1, bfr[blk]);
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t w0 = rp[r * (kInPitch / 4)], w1 = rp[r * (kInPitch / 4) + 1], w2 = rp[r * (kInPitch / 4) + 2];
+                        A[r] = __funnelshift_r(w0, w1, 24);
+                        B[r] = __funnelshift_r(w1, w2, 8);
                     }
-                    int pe[4], po[4];
+                    uint32_t va[4], vb[4];
 #pragma unroll
-                    for (int ol = 0; ol < 4; ol++) {
-                        pe[ol] = max4(c[ol][0], c[ol][1], c[4 + ol][0], c[4 + ol][1]);
-                        po[ol] = max4(c[ol][2], c[ol][3], c[4 + ol][2], c[4 + ol][3]);
+                    for (int o4 = 0; o4 < 4; o4++) {
+                        int pa[4], pb[4];
+#pragma unroll
+                        for (int oo = 0; oo < 4; oo++) {
+                            const int o = o4 * 4 + oo;
+                            const uint32_t l0 = P.w0[o][0], l1 = P.w0[o][1], l2 = P.w0[o][2];
+                            const uint32_t h0 = P.w0[o][3], h1 = P.w0[o][4], h2 = P.w0[o][5];
+                            int a00 = dp4a_u8s8(A[0], l0, dp4a_u8s8(A[1], l1, dp4a_u8s8(A[2], l2, 0)));
+                            int a01 = dp4a_u8s8(A[0], h0, dp4a_u8s8(A[1], h1, dp4a_u8s8(A[2], h2, 0)));
+                            int a10 = dp4a_u8s8(A[1], l0, dp4a_u8s8(A[2], l1, dp4a_u8s8(A[3], l2, 0)));
+                            int a11 = dp4a_u8s8(A[1], h0, dp4a_u8s8(A[2], h1, dp4a_u8s8(A[3], h2, 0)));
+                            int b00 = dp4a_u8s8(B[0], l0, dp4a_u8s8(B[1], l1, dp4a_u8s8(B[2], l2, 0)));
+                            int b01 = dp4a_u8s8(B[0], h0, dp4a_u8s8(B[1], h1, dp4a_u8s8(B[2], h2, 0)));
+                            int b10 = dp4a_u8s8(B[1], l0, dp4a_u8s8(B[2], l1, dp4a_u8s8(B[3], l2, 0)));
+                            int b11 = dp4a_u8s8(B[1], h0, dp4a_u8s8(B[2], h1, dp4a_u8s8(B[3], h2, 0)));
+                            pa[oo] = max4(a00, a01, a10, a11);
+                            pb[oo] = max4(b00, b01, b10, b11);
+                        }
+                        va[o4] = act_pack4(pa[0], pa[1], pa[2], pa[3], P.shift0);
+                        vb[o4] = act_pack4(pb[0], pb[1], pb[2], pb[3], P.shift0);
                     }
-                    const uint32_t we = act_pack4(pe[0], pe[1], pe[2], pe[3], P.shift0);
-                    const uint32_t wo = act_pack4(po[0], po[1], po[2], po[3], P.shift0);
-                    // window 2g+16f -> halo column odd (plane 1, index g+8f); window +1 -> even plane, index g+8f+1
-                    *reinterpret_cast<uint32_t*>(row + kA1Q + f * 128) = we;
-                    *reinterpret_cast<uint32_t*>(row + 16 + f * 128) = wo;
+                    // window 2*lane -> halo column 2*lane+1 (odd plane, index lane); window 2*lane+1 -> column 2*lane+2
+                    // (even plane, index lane+1): both 16-byte stores are contiguous across the warp
+                    uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P;
+                    *reinterpret_cast<uint4*>(row + kA1Q + lane * 16) = make_uint4(va[0], va[1], va[2], va[3]);
+                    *reinterpret_cast<uint4*>(row + (lane + 1) * 16) = make_uint4(vb[0], vb[1], vb[2], vb[3]);
                     if (P.dump_l0) {                     // debug / register-protocol path: BRAM channels 0-15
-                        uint8_t* d = P.dump_l0 + (size_t)img * 65536 + (size_t)(4 * t) * 4096 + yp * 64 + 2 * g + 16 * f;
+                        uint8_t* d = P.dump_l0 + (size_t)img * 65536 + yp * 64 + 2 * lane;
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            d[c * 4096] = (uint8_t)(va[c >> 2] >> (8 * (c & 3)));
+                            d[c * 4096 + 1] = (uint8_t)(vb[c >> 2] >> (8 * (c & 3)));
+                        }
+                    }
+                } else {
+                    // ---- mma.sync m16n8k16: A row = one 2x2 pooling window, K = its 4x4 input patch (k = 4*patch row +
+                    // patch column), N = 8 columns = (4 out-channels) x (horizontal member px); 8 column blocks = (vertical
+                    // member py) x (oc%4).  Lane (g,t) ends up with all four members of window g (and g+8) for out-channels
+                    // 4t..4t+3: thread-local pool, one packed word of the act1 vector.  4 fragments of 16 windows per row
+                    // (even windows in rows 0-7, odd ones in rows 8-15: both 128-byte stores are contiguous in their plane).
+                    // Patch row t of windows 2g+16f (a0) and 2g+16f+1 (a1): image row 2yp-1+t, columns 4g+32f-1 .. +4 ----
+                    const uint32_t* rp = in_w + (2 * yp + t) * (kInPitch / 4) + g + 3;
+                    uint8_t* row = smem + kOffA1 + (yp + 1) * kA1P + g * 16 + t * 4;
+#pragma unroll
+                    for (int f = 0; f < 4; f++) {
+                        const uint32_t w0 = rp[8 * f], w1 = rp[8 * f + 1], w2 = rp[8 * f + 2];
+                        const uint32_t a0 = __funnelshift_r(w0, w1, 24), a1 = __funnelshift_r(w1, w2, 8);
+                        int c[8][4];
+#pragma unroll
+                        for (int blk = 0; blk < 8; blk++) {
+                            c[blk][0] = c[blk][1] = c[blk][2] = c[blk][3] = 0;
+                            imma_16816(c[blk], a0, a1, bfr[blk]);
+                        }
+                        int pe[4], po[4];
 #pragma unroll
                         for (int ol = 0; ol < 4; ol++) {
-                            d[ol * 4096] = (uint8_t)(we >> (8 * ol));
-                            d[ol * 4096 + 1] = (uint8_t)(wo >> (8 * ol));
+                            pe[ol] = max4(c[ol][0], c[ol][1], c[4 + ol][0], c[4 + ol][1]);
+                            po[ol] = max4(c[ol][2], c[ol][3], c[4 + ol][2], c[4 + ol][3]);
+                        }
+                        const uint32_t we = act_pack4(pe[0], pe[1], pe[2], pe[3], P.shift0);
+                        const uint32_t wo = act_pack4(po[0], po[1], po[2], po[3], P.shift0);
+                        // window 2g+16f -> halo column odd (plane 1, index g+8f); window +1 -> even plane, index g+8f+1
+                        *reinterpret_cast<uint32_t*>(row + kA1Q + f * 128) = we;
+                        *reinterpret_cast<uint32_t*>(row + 16 + f * 128) = wo;
+                        if (P.dump_l0) {                 // debug / register-protocol path: BRAM channels 0-15
+                            uint8_t* d = P.dump_l0 + (size_t)img * 65536 + (size_t)(4 * t) * 4096 + yp * 64 + 2 * g + 16 * f;
+#pragma unroll
+                            for (int ol = 0; ol < 4; ol++) {
+                                d[ol * 4096] = (uint8_t)(we >> (8 * ol));
+                                d[ol * 4096 + 1] = (uint8_t)(wo >> (8 * ol));
+                            }
                         }
                     }
                 }
+                if (warp == 0) TRACE(2, 2); else if (warp == kL0Warps - 1) TRACE(3, 2);
                 if (yp <= 32 && yp + kL0Warps > 32) {    // this warp's share of pooled rows 0-32 (act1 rows 0-33) is written
                     fence_async_smem();                  // generic-proxy writes -> visible to the MMA (async proxy)
                     __syncwarp();
@@ -393,7 +406,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar(kBarA1BotReady)); mbar_arrive(bar(kBarInFree0 + slot)); }
         }
-#endif
+        if (warp == 0) TRACE_END(2); else if (warp == kL0Warps - 1) TRACE_END(3);
     } else if (warp < kWarpMma) {
         // =============== epilogue warps ==========================================================================
         const int e = warp - kL0Warps;
@@ -409,8 +422,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int t = 0; t < 8; t++) {
                 const int h = t & 1, i0 = (t >> 2) * 16, j0 = (t & 3) * 8;
+                if (e == 0) TRACE(1, 10 + t);
                 wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
                 uses[h]++;
+                if (e == 0) TRACE(1, 20 + t);
                 tc_fence_after();
                 const int i = i0 + (L >> 3), j = j0 + (L & 7);
 #pragma unroll
@@ -448,10 +463,14 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                         for (int c = 0; c < 16; c++) d[c * 1024] = (uint8_t)(ww[c >> 2] >> (8 * (c & 3)));
                     }
                 }
+                if (t >= 6) {
+                    // layer-2 block 0 reads act2 columns 0-16 only: everything but tile 7 (rows 16-31, columns 24-31),
+                    // so it can start while tile 7 is still being drained
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(t == 6 ? kBarA2ReadyA : kBarA2ReadyB));
+                }
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarA2Ready));
 
             // ---- layer 2: 2 blocks of 128 pooling windows x 4 parities; -> staging (CHW) -> one 16 KiB TMA store ----
             if (k > 0) {                                 // the previous image's store must have finished reading staging
@@ -461,8 +480,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
                 const int h = s, j0 = s * 8;
+                if (e == 0) TRACE(1, 40 + s);
                 wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
                 uses[h]++;
+                if (e == 0) TRACE(1, 50 + s);
                 tc_fence_after();
                 const int i = L >> 3, j = j0 + (L & 7);
 #pragma unroll
@@ -499,6 +520,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
         }
         if (e == 0 && lane == 0) bulk_store_wait_all();
+        if (e == 0) TRACE_END(1);
     } else if (warp == kWarpMma) {
         // =============== MMA issue: the whole warp walks the schedule, one elected lane issues ====================
         wait_or_flag(bar(kBarW), 0, kErrWeightTimeout);
@@ -509,10 +531,13 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int t = 0; t < 8; t++) {
                 const int h = t & 1, ty = t >> 2, tx = t & 3;
+                TRACE(0, 10 + t);
                 if (t == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
                 if (t == 4) wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
+                TRACE(0, 20 + t);
                 wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
                 uses[h]++;
+                TRACE(0, 30 + t);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tm + h * 256;
@@ -530,12 +555,14 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 __syncwarp();
             }
             // ---- layer 2: 2 blocks x 4 parities x 9 taps, N = 64 ----
-            wait_or_flag(bar(kBarA2Ready), (uint32_t)k & 1, kErrAct2Timeout);
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
                 const int h = s, j0 = s * 8;
+                TRACE(0, 40 + s);
+                wait_or_flag(bar(s ? kBarA2ReadyB : kBarA2ReadyA), (uint32_t)k & 1, kErrAct2Timeout);
                 wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
                 uses[h]++;
+                TRACE(0, 50 + s);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t a0 = umma_desc(s_base + kOffA2 + j0 * 16, kA2C, 2 * kA2P);
@@ -554,8 +581,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                     umma_commit(bar(kBarTmFull0 + h));
                 }
                 __syncwarp();
+                TRACE(0, 60 + s);
             }
         }
+        TRACE_END(0);
     } else {
         // =============== TMA loads: weights once, then every image two ahead of its consumer ======================
         if (elect_one()) {
@@ -578,6 +607,12 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     // ---- teardown ---------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+#ifdef CNNACC_TRACE
+    if (blockIdx.x == 0 && tid == 0)
+        for (int r = 0; r < kTraceRoles; r++)
+            for (int i = 0; i < trace_cnt[r]; i++)
+                printf("TRACE %d %d %u\n", r, (int)(trace_buf[r * kTraceMax + i] >> 24), trace_buf[r * kTraceMax + i] & 0xFFFFFFu);
+#endif
     if (tid == 0 && *s_err) {
         atomicOr(P.status, *s_err);
         *reinterpret_cast<volatile int*>(P.status_host) = *s_err;
