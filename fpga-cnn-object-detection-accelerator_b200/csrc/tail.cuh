@@ -124,18 +124,31 @@ classify_bbox_kernel(const uint8_t* __restrict__ feats, const float* __restrict_
 #pragma unroll
     for (int w8 = 1; w8 < 8; w8++) m = fmaxf(m, s_red[w8]);
     if (m > 0.f) cam = __fdiv_rn(cam, m);
-    s_cam[t] = cam;
-    __syncthreads();
 
-    // rank by counting (stable on index): sorted[178] and sorted[179] bracket the 70th percentile
-    int rank = 0;
-#pragma unroll 8
-    for (int j = 0; j < 256; j++) {
-        float v = s_cam[j];
-        rank += (v < cam) || (v == cam && j < t);
+    // 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort, one value per thread:
+    // strides < 32 exchange by shuffle, strides >= 32 through shared memory (36 compare-exchange stages instead of
+    // the 256-step rank-by-counting loop this replaced).
+    float v = cam;
+#pragma unroll
+    for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            float o;
+            if (j >= 32) {
+                __syncthreads();                         // previous readers of s_cam are done
+                s_cam[t] = v;
+                __syncthreads();
+                o = s_cam[t ^ j];
+            } else {
+                o = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool up = ((t & k) == 0);              // ascending block
+            const bool lower = ((t & j) == 0);           // this thread keeps the smaller one in an ascending block
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
     }
-    if (rank == 178) s_lohi[0] = cam;
-    if (rank == 179) s_lohi[1] = cam;
+    if (t == 178) s_lohi[0] = v;
+    if (t == 179) s_lohi[1] = v;
     __syncthreads();
     const float lo = s_lohi[0], hi = s_lohi[1];
     float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
