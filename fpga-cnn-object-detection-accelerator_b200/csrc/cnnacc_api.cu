@@ -312,7 +312,10 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
 
     // host pointers: 3-slot pipeline, slot streams overlap H2D / kernels / D2H
     CU(h, cudaStreamSynchronize(h->stream));
-    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), ((size_t)64 << 20) / in_sz)));
+    // chunk = what one slot stages: small enough that the un-overlapped first H2D / last D2H are a small part of the
+    // call, large enough to fill the GPU (CNNACC_HOST_CHUNK_MB overrides the 32 MiB default for tuning; measured 4..64 MiB: tools/e2e_sweep.py)
+    static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 32); }();
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (chunk_mb << 20) / in_sz)));
     if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
     int64_t ci = 0;
     for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
