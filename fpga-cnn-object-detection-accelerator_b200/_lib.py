@@ -24,6 +24,7 @@ SYMBOLS = {
     "cnnacc_set_shifts": (_c.c_int, [_H, _c.c_int, _c.c_int, _c.c_int]),
     "cnnacc_get_shifts": (_c.c_int, [_H, _c.POINTER(_c.c_int)]),
     "cnnacc_pack_weights_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "cnnacc_tile_plan_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "cnnacc_run_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
     "cnnacc_load_image": (_c.c_int, [_H, _c.c_void_p, _c.c_size_t]),
     "cnnacc_start": (_c.c_int, [_H]),

@@ -12,6 +12,7 @@
 #include "conv_direct.cuh"
 #include "conv_fused.cuh"
 #include "tail.cuh"
+#include "tiling.cuh"
 #include "weights_pack.h"
 
 using namespace cnnacc;
@@ -83,6 +84,12 @@ int grow(cnnacc_handle* h, uint8_t** p, size_t* cap, size_t need) {
 
 bool valid_hw(int H, int W) { return H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && H <= 8192 && W <= 8192; }
 
+// Sizes from 128 up (other than 128x128 itself) run as overlapping windows through the fused kernel.
+bool tiled_ok(const cnnacc_handle* h, int H, int W, uint32_t flags) {
+    return H >= CNNACC_IMG && W >= CNNACC_IMG && !(H == CNNACC_IMG && W == CNNACC_IMG) && h->fused.ready &&
+           !(flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS));
+}
+
 // One layer of the generic per-layer path on `stream`.
 int launch_direct_layer(cnnacc_handle* h, cudaStream_t stream, int layer, const uint8_t* in, uint8_t* out,
                         int64_t n, int H, int W) {
@@ -108,6 +115,20 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
         if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
         return 0;
     }
+    if (tiled_ok(h, H, W, flags)) {
+        // larger images: overlapping 128x128 windows through the fused kernel (tiling.cuh); d_l0 / d_l1 hold the windows
+        // and their 16x16 feature tiles
+        const TilePlan py = make_tile_plan(H / 8), px = make_tile_plan(W / 8);
+        const int64_t n_t = n * py.n * px.n;
+        if (n_t > 0x7fffffff) return fail(h, CNNACC_ERR_ARG, "too many tiles in one chunk");
+        gather_tiles_kernel<<<(unsigned)n_t, 256, 0, stream>>>(d_imgs, d_l0, H, W, py, px);
+        int rc = launch_fused(h->fused, stream, d_l0, n_t, d_l1, h->shifts, h->sm_count, nullptr, nullptr);
+        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch (tiled): ") + cudaGetErrorString((cudaError_t)rc));
+        scatter_features_kernel<<<(unsigned)n_t, 256, 0, stream>>>(d_l1, d_feats, H / 8, W / 8, py, px);
+        h->launches += 3;
+        CU(h, cudaGetLastError());
+        return 0;
+    }
     int rc;
     if ((rc = launch_direct_layer(h, stream, 0, d_imgs, d_l0, n, H, W))) return rc;
     if ((rc = launch_direct_layer(h, stream, 1, d_l0, d_l1, n, H / 2, W / 2))) return rc;
@@ -128,8 +149,10 @@ int64_t chunk_images(int H, int W) {
 
 int ensure_maps(cnnacc_handle* h, int64_t n, int H, int W) {
     int rc;
-    if ((rc = grow(h, &h->d_l0, &h->cap_l0, (size_t)n * 16 * (H / 2) * (W / 2)))) return rc;
-    if ((rc = grow(h, &h->d_l1, &h->cap_l1, (size_t)n * 32 * (H / 4) * (W / 4)))) return rc;
+    // per-layer path: the two intermediate maps; tiled path: the 128x128 windows and their feature tiles
+    const size_t tiles = (H >= CNNACC_IMG && W >= CNNACC_IMG) ? (size_t)n * tiles_per_dim(H / 8) * tiles_per_dim(W / 8) * 16384 : 0;
+    if ((rc = grow(h, &h->d_l0, &h->cap_l0, std::max((size_t)n * 16 * (H / 2) * (W / 2), tiles)))) return rc;
+    if ((rc = grow(h, &h->d_l1, &h->cap_l1, std::max((size_t)n * 32 * (H / 4) * (W / 4), tiles)))) return rc;
     return 0;
 }
 
@@ -281,6 +304,14 @@ int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint32_t* w0,
     static_assert(CNNACC_PACK_B1_BYTES == kB1Bytes && CNNACC_PACK_B2_BYTES == kB2Bytes, "header out of date");
     fused_pack_weights(weights_bin, reinterpret_cast<uint32_t(*)[6]>(w0), reinterpret_cast<uint32_t(*)[32]>(w0 + 96), b1, b2);
     return CNNACC_OK;
+}
+
+int cnnacc_tile_plan_host(int n_out, int* origin, int* first, int* end, int cap) {
+    if (n_out < 16 || n_out > 1024 || !origin || !first || !end) return CNNACC_ERR_ARG;
+    const TilePlan p = make_tile_plan(n_out);
+    if (p.n > cap) return CNNACC_ERR_ARG;
+    for (int i = 0; i < p.n; i++) { origin[i] = p.g[i]; first[i] = p.s[i]; end[i] = p.e[i]; }
+    return p.n;
 }
 
 int cnnacc_get_shifts(const cnnacc_handle* h, int* s3) {

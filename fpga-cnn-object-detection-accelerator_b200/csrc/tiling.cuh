@@ -1,0 +1,84 @@
+// tiling.cuh -- images larger than 128x128 through the fused 128x128 kernel, by overlapping tiles with halo recompute.
+//
+// The reference handles other sizes only in its numpy twin (arm_benchmark.py:76-121, H,W-generic); the FPGA solves the
+// "map does not fit on chip" problem by spatial tiling through its accumulators (layer_fsm.v:66-75,205-213).  Here a
+// tile is a 128x128 window = 16x16 outputs of the three-layer stack.  Output o (one dimension) depends on input pixels
+// 8o-7 .. 8o+14 and on the zero padding each layer applies at the IMAGE border.  Inside a window the kernel pads at the
+// WINDOW border instead, so the outermost output row/column of a window is only right where the window border is the
+// image border.  Windows therefore advance by 14 outputs and overlap by 2:
+//   tile t covers outputs [14t, 14t+14), window origin g(t) = clamp(14t-1, 0, Ho-16) outputs = 8*g pixels.
+// Windows therefore overlap by 2 outputs; along one dimension (Ho outputs, window origin g in outputs = 8g pixels):
+//   window 0: g = 0, owns outputs 0..14; then each window starts one output before the first output it owns and owns
+//   14; the last window is pushed back to g = Ho-16 and owns everything up to Ho-1.
+// Cost: (16/14)^2 = 1.31x recompute in the limit (512x512: 25 windows instead of 16).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cnnacc {
+
+constexpr int kMaxTilesPerDim = 80;                      // 8192 / 8 / 14 = 73.2
+
+// Window plan along one dimension, built on the host and passed by value to the kernels.
+struct TilePlan {
+    int n;                                               // windows
+    short g[kMaxTilesPerDim];                            // window origin (outputs)
+    short s[kMaxTilesPerDim], e[kMaxTilesPerDim];        // owned outputs [s, e)
+};
+
+inline TilePlan make_tile_plan(int Ho) {
+    TilePlan p{};
+    int start = 0;
+    while (start < Ho && p.n < kMaxTilesPerDim) {
+        int g = start - 1;
+        if (g > Ho - 16) g = Ho - 16;
+        if (g < 0) g = 0;
+        const int hi = (g == Ho - 16) ? 15 : 14;         // last valid local output of this window
+        int end = g + hi + 1;
+        if (end > Ho) end = Ho;
+        p.g[p.n] = (short)g; p.s[p.n] = (short)start; p.e[p.n] = (short)end;
+        p.n++;
+        start = end;
+    }
+    return p;
+}
+inline int tiles_per_dim(int Ho) { return make_tile_plan(Ho).n; }
+
+// tiles[(img*nty + ty)*ntx + tx][128][128] <- imgs[img][8*gy .. +128][8*gx .. +128]
+__global__ void __launch_bounds__(256)
+gather_tiles_kernel(const uint8_t* __restrict__ imgs, uint8_t* __restrict__ tiles, int H, int W,
+                    const __grid_constant__ TilePlan py, const __grid_constant__ TilePlan px)
+{
+    const int64_t tile = blockIdx.x;
+    const int ntx = px.n, nty = py.n;
+    const int tx = (int)(tile % ntx), ty = (int)((tile / ntx) % nty);
+    const int64_t img = tile / ((int64_t)ntx * nty);
+    const int oy = 8 * py.g[ty], ox = 8 * px.g[tx];
+    const uint8_t* src = imgs + (size_t)img * H * W + (size_t)oy * W + ox;
+    uint2* dst = reinterpret_cast<uint2*>(tiles + (size_t)tile * 16384);
+    for (int i = threadIdx.x; i < 128 * 16; i += 256) {      // 16 x 8 bytes per row (origins are multiples of 8 pixels)
+        const int r = i >> 4, c = i & 15;
+        dst[i] = *reinterpret_cast<const uint2*>(src + (size_t)r * W + c * 8);
+    }
+}
+
+// feats[img][64][Ho][Wo] <- the outputs each tile owns out of tfeat[tile][64][16][16]
+__global__ void __launch_bounds__(256)
+scatter_features_kernel(const uint8_t* __restrict__ tfeat, uint8_t* __restrict__ feats, int Ho, int Wo,
+                        const __grid_constant__ TilePlan py, const __grid_constant__ TilePlan px)
+{
+    const int64_t tile = blockIdx.x;
+    const int ntx = px.n, nty = py.n;
+    const int tx = (int)(tile % ntx), ty = (int)((tile / ntx) % nty);
+    const int64_t img = tile / ((int64_t)ntx * nty);
+    const int gy = py.g[ty], gx = px.g[tx];
+    const int y0 = py.s[ty], ny = py.e[ty] - y0, x0 = px.s[tx], nx = px.e[tx] - x0;
+    const uint8_t* src = tfeat + (size_t)tile * 16384;
+    uint8_t* dst = feats + (size_t)img * 64 * Ho * Wo;
+    for (int i = threadIdx.x; i < 64 * ny * nx; i += 256) {
+        const int x = i % nx, y = (i / nx) % ny, c = i / (nx * ny);
+        dst[((size_t)c * Ho + y0 + y) * Wo + x0 + x] = src[c * 256 + (y0 + y - gy) * 16 + (x0 + x - gx)];
+    }
+}
+
+}  // namespace cnnacc

@@ -78,10 +78,17 @@ int cnnacc_get_shifts(const cnnacc_handle *h, int *s3);
 #define CNNACC_PACK_B2_BYTES 18432
 int cnnacc_pack_weights_host(const uint8_t *weights_bin, size_t n, uint32_t *w0, uint8_t *b1, uint8_t *b2);
 
+/* Host-only view of the window plan used for images larger than 128x128 (csrc/tiling.cuh): along one dimension with
+ * n_out = size/8 outputs, window i starts at output origin[i] (pixel 8*origin[i]) and owns outputs [first[i], end[i]).
+ * Returns the number of windows (<= cap) or a negative code.  The FPGA's analogue is the 4-tile drain of layer 0
+ * (layer_fsm.v:66-75,205-213); tests/ check that the plan owns every output exactly once and only where it is valid. */
+int cnnacc_tile_plan_host(int n_out, int *origin, int *first, int *end, int cap);
+
 /* ---- the hot path: batched conv stack ------------------------------------------------------
  * Replaces cnn_infer (arm_cnn.c:159-198) / FPGAEngine.run (realtime_detect.py:313-363) for n images.
  *   imgs  : [n][H][W] u8          feats : [n][64][H/8][W/8] u8   (CHW per image, arm_cnn.c:64-65)
- * H, W multiples of 16.  128x128 runs the fused sm_100a kernel; other sizes the generic kernels.
+ * H, W multiples of 16.  128x128 runs the fused sm_100a kernel; larger sizes run as overlapping 128x128 windows through
+ * the same kernel (halo recompute, csrc/tiling.cuh); smaller ones (and CNNACC_FLAG_DIRECT) the generic per-layer kernels.
  * Host pointers: the call stages through pinned buffers, overlapping H2D / compute / D2H, and
  * returns when feats is complete.  Device pointers: asynchronous on the handle's stream. */
 int cnnacc_run_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n, int H, int W,

@@ -59,3 +59,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_window_plan_for_large_images(lib):
+    """csrc/tiling.cuh: every output owned by exactly one 128-pixel window, never by a window's outermost row/column unless
+    that is the image border (where the kernel's zero padding is the real padding)."""
+    buf = lambda: np.zeros(80, np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for n_out in list(range(16, 130)) + [256, 1000, 1024]:
+        g, s, e = buf(), buf(), buf()
+        n = lib.cnnacc_tile_plan_host(n_out, p(g), p(s), p(e), 80)
+        assert n >= 1
+        owned = np.zeros(n_out, np.int32)
+        for i in range(n):
+            assert 0 <= g[i] <= n_out - 16 and s[i] < e[i]
+            for o in range(s[i], e[i]):
+                loc = o - g[i]
+                assert 0 <= loc <= 15 and (loc >= 1 or g[i] == 0) and (loc <= 14 or g[i] == n_out - 16)
+                owned[o] += 1
+        assert (owned == 1).all()
+    assert lib.cnnacc_tile_plan_host(8, p(buf()), p(buf()), p(buf()), 80) == fc._lib.ERR_ARG

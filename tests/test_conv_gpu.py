@@ -87,6 +87,22 @@ def test_generic_sizes(case, acc, shipped_weights, conv_golden):
     assert np.array_equal(got.reshape(64, -1), conv_golden[case["name"]])
 
 
+@pytest.mark.parametrize("H,W", [(128, 256), (144, 208), (384, 128), (240, 336), (512, 512)])
+def test_tiled_windows_vs_oracle_and_direct(H, W, acc, port, shipped_weights):
+    """Sizes above 128x128 run as overlapping 128x128 windows through the fused kernel (csrc/tiling.cuh): every output
+    must equal the oracle's full-image result (halo recompute, image-border padding) and the per-layer kernels'."""
+    n = 3
+    for wt, sh, kind in ((shipped_weights, (7, 10, 11), ("rng", 31)), (inputs.make_weights(("rng", 32)), (9, 12, 13), ("smooth", 33))):
+        acc.load_weights(wt)
+        acc.set_shifts(*sh)
+        imgs = inputs.make_images(kind, n, H, W)
+        got = acc.run_batch(imgs)
+        assert got.shape == (n, 64, H // 8, W // 8)
+        want = oracle.port_infer_batch(port, imgs, wt, sh, H, W)
+        assert np.array_equal(got.reshape(n, 64, -1), want), np.argwhere(got.reshape(n, 64, -1) != want)[:5]
+        assert np.array_equal(acc.run_batch(imgs, direct=True), got)
+
+
 def test_fused_equals_direct_at_scale(acc, shipped_weights):
     """Full-size property check: the fused kernel and the per-layer kernels agree on 4096 images (config 2)."""
     acc.load_weights(shipped_weights)
