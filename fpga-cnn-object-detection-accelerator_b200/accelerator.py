@@ -300,6 +300,44 @@ class ARMEngine:
         return self.output_buf.reshape(N_CH, FM).copy(), conv_ms, 0.0
 
 
+class Classifier:
+    """pynq_inference.py:292-347 on the GPU: classify((64,256) u8) -> (class_index, class_name, confidence, probabilities).
+
+    The reference takes the exact-integer bin mean and then divides by 255; the tail kernel computes S/4080 in one
+    rounding, which is the same fp32 value.  Weights must be (num_classes, 1024) -- the (6,64) GAP file the reference
+    ships does not fit its own classify() either."""
+
+    def __init__(self, fc_weight_path, fc_bias_path, classes_path=None, device=0):
+        import json
+        load = lambda x: np.load(x) if isinstance(x, (str, os.PathLike)) else np.asarray(x)
+        self.weight = np.ascontiguousarray(load(fc_weight_path), dtype=np.float32)
+        self.bias = np.ascontiguousarray(load(fc_bias_path), dtype=np.float32)
+        self.num_classes = self.weight.shape[0]
+        self.class_names = None
+        if classes_path and os.path.exists(classes_path):
+            with open(classes_path) as f:
+                self.class_names = json.load(f)
+        self._acc = CNNAccelerator(device=device)
+        self._acc.load_classifier(self.weight, self.bias)     # ValueError unless (n_cls, 1024) + (n_cls,)
+
+    def classify(self, features):
+        cls, probs, _ = self._acc.classify_batch(np.asarray(features, dtype=np.uint8).reshape(1, 64, 256))
+        idx = int(cls[0])
+        name = self.class_names[idx] if self.class_names else str(idx)
+        return idx, name, float(probs[0, idx]), probs[0]
+
+
+def dump_features(acc, images, labels, names, output, shifts=None):
+    """The .npz the reference's feature dumpers write (dump_arm_features.py:162-170, dump_fpga_features.py:116-120):
+    features (N,64,256) u8, labels, names, shifts.  `images` is [N,128,128] u8; one batched call instead of a loop."""
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    if shifts is not None:
+        acc.set_shifts(*shifts)
+    feats = acc.run_batch(images).reshape(len(images), N_CH, FM)
+    np.savez(output, features=feats, labels=np.array(labels), names=list(names), shifts=np.array(acc.get_shifts()))
+    return feats
+
+
 _tail_acc = {}
 
 

@@ -100,3 +100,25 @@ def test_full_pipeline_matches_two_step(conv_golden, shipped_weights):
     cls2, probs2, bbox2 = a.classify_batch(conv_golden["rng_shipped_mid"])
     assert np.array_equal(cls, cls2) and np.array_equal(probs, probs2) and np.array_equal(bbox, bbox2)
     a.close()
+
+
+def test_classifier_object_and_feature_dump(tmp_path, conv_golden, shipped_weights):
+    """pynq_inference.Classifier.classify surface and the dumpers' .npz format (dump_arm_features.py:162-170)."""
+    import fpga_cnn_b200 as fc
+    fw, fb = inputs.make_fc()
+    clf = fc.Classifier(fw, fb)
+    feat = conv_golden["rng_shipped_mid"][0]
+    idx, name, conf, probs = clf.classify(feat)
+    want_c, want_p, _, _ = np_oracle.classify_vec(feat, fw, fb)
+    assert idx == want_c and name == str(want_c) and np.allclose(probs, want_p, rtol=1e-5, atol=1e-6) and abs(conf - want_p[want_c]) < 1e-5
+    with pytest.raises(ValueError):
+        fc.Classifier(np.zeros((6, 64), np.float32), np.zeros(6, np.float32))      # the shipped GAP-shaped file
+    acc = fc.CNNAccelerator(device=0)
+    acc.load_weights(shipped_weights)
+    imgs = inputs.make_images(("rng", 1), 8)
+    out = tmp_path / "feats.npz"
+    fc.dump_features(acc, imgs, labels=list(range(8)), names=[f"img{i}" for i in range(8)], output=out, shifts=(7, 10, 11))
+    z = np.load(out)
+    assert z["features"].shape == (8, 64, 256) and z["features"].dtype == np.uint8
+    assert np.array_equal(z["features"], conv_golden["rng_shipped_mid"]) and list(z["shifts"]) == [7, 10, 11]
+    assert list(z["labels"]) == list(range(8)) and list(z["names"]) == [f"img{i}" for i in range(8)]
