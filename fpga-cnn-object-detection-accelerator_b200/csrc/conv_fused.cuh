@@ -5,7 +5,8 @@
 // (rtl/core/cnn_acc_top.v).  Like the FPGA design, every intermediate map stays on chip: one CTA per SM
 // keeps an image's maps in shared memory and HBM sees 16 KiB of pixels in and 16 KiB of features out.
 //
-//   layer 0  (1->16, 128x128, K=9)    CUDA cores: dp4a.u32.s32, 2x2 pool in registers, -> act1 (smem)
+//   layer 0  (1->16, 128x128, K=9)    half the rows on the dp4a pipe (dp4a.u32.s32), half on warp-level int8 MMA
+//                                     (mma.sync m16n8k16); 2x2 pool in registers, -> act1 (smem)
 //   layer 1  (16->32, 64x64, K=144)   tcgen05.mma kind::i8 (A = u8 activations, B = s8 weights, D = s32 in TMEM)
 //   layer 2  (32->64, 32x32, K=288)   tcgen05.mma kind::i8
 //   each followed by >>shift, ReLU/saturate (arm_cnn.c:127-135) and 2x2 max-pool (arm_cnn.c:115-143),
@@ -25,13 +26,14 @@
 //            planes (LBO = plane stride), 9 MMAs, N = 64; the four parities go to four TMEM column groups.
 // These descriptor forms were verified on a B200 by tools/probe_umma.cu (profiles/r1_probe_umma_dp4a_tmem.txt).
 //
-// Warp roles (18 warps, 1 CTA/SM).  The dp4a pipe (layer 0) and the tensor pipe (layers 1-2) run concurrently
-// on DIFFERENT images: while the tensor core and the epilogue warps finish image k, the layer-0 warps already
-// produce image k+1 into the half of act1 the MMAs have released.
-//   warps 0-7    layer 0 (dp4a) : input slot -> act1
-//   warps 8-15   epilogues      : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
-//   warp 16      MMA issue (one elected thread), TMEM allocation
-//   warp 17      TMA loads (weights once, then images two ahead)
+// Warp roles (21 warps, 1 CTA/SM).  Layer 0 and the tcgen05 layers run concurrently on DIFFERENT images: while the
+// tensor core and the epilogue warps finish image k, the layer-0 warps already produce image k+1 into the half of
+// act1 the MMAs have released.
+//   warps 0-7    layer 0 on the dp4a pipe : input slot -> act1   (rows w, w+16, w+32, w+48)
+//   warps 8-15   layer 0 on mma.sync      : input slot -> act1
+//   warps 16-19  epilogues : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
+//   warp 20      tcgen05 MMA issue (whole warp walks the schedule, one elected lane issues), TMEM allocation,
+//                TMA loads (weights once, then images two ahead)
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
@@ -100,8 +102,8 @@ constexpr int kTraceMax = 200, kTraceRoles = 4;
 constexpr int kL0Dp4aWarps = CNNACC_L0_DP4A_WARPS;
 constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
 static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
-constexpr int kWarpMma = kL0Warps + kEpiWarps, kWarpTma = kWarpMma + 1;
-constexpr int kFusedThreads = (kWarpTma + 1) * 32;    // 576
+constexpr int kWarpMma = kL0Warps + kEpiWarps;       // the last warp: MMA issue and TMA loads
+constexpr int kFusedThreads = (kWarpMma + 1) * 32;    // 21 warps = 672: leaves 96 registers per thread
 constexpr uint32_t kTmemCols = 512;
 
 // mbarrier slots (8 bytes each) at kOffBar
@@ -230,6 +232,8 @@ __device__ __forceinline__ uint32_t act_u8(int v, int shift) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------
+// Register budget: each SM sub-partition has 16 384 registers and 21 warps put 6 on one of them, so 80 per thread
+// (6 x 80 x 32 = 15 360) is the most that launches; 96 would need <= 20 warps.
 __global__ void __launch_bounds__(kFusedThreads, 1)
 conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FusedParams P)
 {
@@ -415,7 +419,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         const int g0 = e >> 2;
         const int L = q * 32 + lane;
         const uint32_t t_lane = tm + ((uint32_t)(q * 32) << 16);
-        uint32_t uses[2] = {0, 0};                       // completed uses of each TMEM half (same sequence as the MMA warp)
+        uint32_t use0 = 0, use1 = 0;                     // completed uses of each TMEM half (scalars: an array indexed by the
+                                                         // half would live in local memory on the critical path)
         for (int k = 0; k < n_local; k++) {
             const int img = (int)blockIdx.x + k * (int)gridDim.x;
             // ---- layer 1: 8 tiles of 128 pooling windows; TMEM -> pool -> shift/ReLU/saturate -> act2 (smem) ----
@@ -423,8 +428,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             for (int t = 0; t < 8; t++) {
                 const int h = t & 1, i0 = (t >> 2) * 16, j0 = (t & 3) * 8;
                 if (e == 0) TRACE(1, 10 + t);
-                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
-                uses[h]++;
+                wait_or_flag(bar(kBarTmFull0 + h), (h ? use1 : use0) & 1, kErrMmaTimeout);
+                if (h) use1++; else use0++;
                 if (e == 0) TRACE(1, 20 + t);
                 tc_fence_after();
                 const int i = i0 + (L >> 3), j = j0 + (L & 7);
@@ -481,8 +486,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             for (int s = 0; s < 2; s++) {
                 const int h = s, j0 = s * 8;
                 if (e == 0) TRACE(1, 40 + s);
-                wait_or_flag(bar(kBarTmFull0 + h), uses[h] & 1, kErrMmaTimeout);
-                uses[h]++;
+                wait_or_flag(bar(kBarTmFull0 + h), (h ? use1 : use0) & 1, kErrMmaTimeout);
+                if (h) use1++; else use0++;
                 if (e == 0) TRACE(1, 50 + s);
                 tc_fence_after();
                 const int i = L >> 3, j = j0 + (L & 7);
@@ -522,10 +527,22 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         if (e == 0 && lane == 0) bulk_store_wait_all();
         if (e == 0) TRACE_END(1);
     } else if (warp == kWarpMma) {
-        // =============== MMA issue: the whole warp walks the schedule, one elected lane issues ====================
+        // =============== MMA issue + TMA loads: the whole warp walks the schedule, one elected lane issues ========
+        // TMA: weights once, then every image two ahead of its consumer (the prefetch of image k+2 is issued when
+        // layer 0 has released image k's slot, which this warp learns while waiting for image k's bottom rows anyway).
+        if (elect_one()) {
+            mbar_expect_tx(bar(kBarW), kB1Bytes + kB2Bytes);
+            bulk_load(s_base + kOffB1, P.b1, kB1Bytes, bar(kBarW));
+            bulk_load(s_base + kOffB2, P.b2, kB2Bytes, bar(kBarW));
+            for (int k = 0; k < 2 && k < n_local; k++) {
+                mbar_expect_tx(bar(kBarInFull0 + k), kInBytes);
+                tma_load_image(s_base + (k ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + k), (int)blockIdx.x + k * (int)gridDim.x);
+            }
+        }
+        __syncwarp();
         wait_or_flag(bar(kBarW), 0, kErrWeightTimeout);
-        uint32_t uses[2] = {0, 0};
         constexpr uint32_t idesc1 = umma_idesc_i8(128), idesc2 = umma_idesc_i8(64);
+        uint32_t use0 = 0, use1 = 0;                     // uses of each TMEM half issued so far
         for (int k = 0; k < n_local; k++) {
             // ---- layer 1: 8 tiles (2 row halves x 4 column blocks) x 8 K-slabs, N = 128 ----
 #pragma unroll 1
@@ -533,10 +550,22 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 const int h = t & 1, ty = t >> 2, tx = t & 3;
                 TRACE(0, 10 + t);
                 if (t == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
-                if (t == 4) wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
+                if (t == 4) {
+                    wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
+                    if (k + 2 < n_local) {               // layer 0 is done with image k: refill its slot with image k+2
+                        const int slot = k & 1;
+                        wait_or_flag(bar(kBarInFree0 + slot), (uint32_t)(k >> 1) & 1, kErrSlotTimeout);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar(kBarInFull0 + slot), kInBytes);
+                            tma_load_image(s_base + (slot ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + slot),
+                                           (int)blockIdx.x + (k + 2) * (int)gridDim.x);
+                        }
+                        __syncwarp();
+                    }
+                }
                 TRACE(0, 20 + t);
-                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
-                uses[h]++;
+                wait_or_flag(bar(kBarTmEmpty0 + h), ((h ? use1 : use0) & 1) ^ 1, kErrEmptyTimeout);   // previous use drained
+                if (h) use1++; else use0++;
                 TRACE(0, 30 + t);
                 tc_fence_after();
                 if (elect_one()) {
@@ -560,8 +589,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 const int h = s, j0 = s * 8;
                 TRACE(0, 40 + s);
                 wait_or_flag(bar(s ? kBarA2ReadyB : kBarA2ReadyA), (uint32_t)k & 1, kErrAct2Timeout);
-                wait_or_flag(bar(kBarTmEmpty0 + h), (uses[h] & 1) ^ 1, kErrEmptyTimeout);
-                uses[h]++;
+                wait_or_flag(bar(kBarTmEmpty0 + h), ((h ? use1 : use0) & 1) ^ 1, kErrEmptyTimeout);
+                if (h) use1++; else use0++;
                 TRACE(0, 50 + s);
                 tc_fence_after();
                 if (elect_one()) {
@@ -585,23 +614,6 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
         }
         TRACE_END(0);
-    } else {
-        // =============== TMA loads: weights once, then every image two ahead of its consumer ======================
-        if (elect_one()) {
-            mbar_expect_tx(bar(kBarW), kB1Bytes + kB2Bytes);
-            bulk_load(s_base + kOffB1, P.b1, kB1Bytes, bar(kBarW));
-            bulk_load(s_base + kOffB2, P.b2, kB2Bytes, bar(kBarW));
-        }
-        __syncwarp();
-        for (int k = 0; k < n_local; k++) {
-            const int slot = k & 1;
-            if (k >= 2) wait_or_flag(bar(kBarInFree0 + slot), (uint32_t)((k >> 1) - 1) & 1, kErrSlotTimeout);
-            if (elect_one()) {
-                mbar_expect_tx(bar(kBarInFull0 + slot), kInBytes);
-                tma_load_image(s_base + (slot ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + slot), (int)blockIdx.x + k * (int)gridDim.x);
-            }
-            __syncwarp();
-        }
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------
