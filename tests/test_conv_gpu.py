@@ -78,6 +78,30 @@ def test_random_batch_vs_oracle(direct, acc, port, shipped_weights):
         assert np.array_equal(got, want), f"trial {trial}: {np.argwhere(got != want)[:5]}"
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 147, 148, 149, 295, 296, 297, 445])
+def test_batch_sizes_around_the_sm_count(n, acc, port, shipped_weights):
+    """The fused kernel is persistent (one CTA per SM, images strided by CTA): CTAs with 1, 2, 3 and 4 images, the
+    2-deep input prefetch and the cross-image pipeline hand-offs all have to line up at every batch size."""
+    acc.load_weights(shipped_weights)
+    acc.set_shifts(7, 10, 11)
+    imgs = inputs.make_images(("rng", 1000 + n), n)
+    got = acc.run_batch(imgs).reshape(n, 64, 256)
+    assert np.array_equal(got, oracle.port_infer_batch(port, imgs, shipped_weights, (7, 10, 11)))
+
+
+def test_random_shift_triples(acc, port, shipped_weights):
+    """Every per-layer shift in 0..31 (the 5-bit AXI register field, pynq_inference.py:226-229), random weights."""
+    rng = np.random.default_rng(77)
+    for trial in range(8):
+        wt = shipped_weights if trial % 2 else inputs.make_weights(("rng", 500 + trial))
+        sh = tuple(int(v) for v in rng.integers(0, 32, 3))
+        imgs = inputs.make_images(("smooth", 600 + trial) if trial % 3 == 0 else ("rng", 600 + trial), 40)
+        acc.load_weights(wt)
+        acc.set_shifts(*sh)
+        got = acc.run_batch(imgs).reshape(40, 64, 256)
+        assert np.array_equal(got, oracle.port_infer_batch(port, imgs, wt, sh)), (trial, sh)
+
+
 @pytest.mark.parametrize("case", inputs.HW_CASES, ids=lambda c: c["name"])
 def test_generic_sizes(case, acc, shipped_weights, conv_golden):
     acc.load_weights(inputs.make_weights(case["weights"], shipped_weights))
