@@ -4,8 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
 One "step" = one pass of the conv stack (128x128 u8 -> 64x16x16 u8, shipped weights.bin, shifts 2/4/6)
-over one batch of B synthetic images per GPU.  `value` is images/s with the batch already resident in HBM;
-`e2e` is the same call through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).
+over one batch of B synthetic images per GPU -- B = 4096 by default, BASELINE.json's configs[1].  The steps walk
+round-robin over enough independent buffer pairs to exceed 2 GiB, so no step finds its data in L2.  `value` is
+images/s with the batches already resident in HBM; `e2e` is the same call through the C ABI with pinned HOST buffers
+(H2D + D2H inside the timed region).  `extra` adds the north_star's batch-65536 throughput, the full pipeline
+(configs[2]) and the batch-1 latency.
 N > 1: launched by torchrun, one rank per GPU, batch sharded by rank with no data-path collective (weak
 scaling: B images per GPU); times are CUDA-event times, max over ranks.
 `--impl reference` times the reference's own arm_cnn.c (oracle/_ref, one process per host core because
@@ -81,31 +84,77 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region.  NVML in a thread (a query takes well under a millisecond,
+    so even a few-millisecond region gets samples); `nvidia-smi -lms` as the fallback (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # nvidia-smi fallback: (t, csv line)
+        self.samples = []        # NVML: (t, sm_mhz, reasons bitmask)
+        self.smax = None
+        self._stop = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid_order = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if uuid_order and all(tok.strip().isdigit() for tok in uuid_order.split(",")):
+                idx = int(uuid_order.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)],
+                                          "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop:
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.time(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t_begin, t_end):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            inreg = [(m, r) for ts, m, r in self.samples if t_begin <= ts <= t_end]
+            if not inreg:                                     # region shorter than one poll: take the nearest sample
+                near = sorted(self.samples, key=lambda x: abs(x[0] - 0.5 * (t_begin + t_end)))[:1]
+                inreg = [(m, r) for _, m, r in near]
+            reasons = sorted({name for _, r in inreg for name, bit in self.REASONS if r & bit})
+            return {"sm_mhz": statistics.median([m for m, _ in inreg]) if inreg else None, "sm_max_mhz": self.smax,
+                    "reasons": reasons, "samples": len(inreg), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -127,7 +176,7 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,8 +238,10 @@ def run_reference_arm(args, weights):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8*s8->s32", "data": "synthetic",
-        "config": {"workload": f"conv_stack_128x128 (arm_cnn.c on host CPU, {cores} processes x {per_core} images per step; "
-                               f"same stack/weights/shifts as the GPU arm's batch {args.batch})"},
+        "config": {"workload": f"configs[1]: 3-layer int8 conv stack, batch {args.batch} synthetic 128x128 images per GPU per step, "
+                               "bit-exact vs arm_cnn.c",
+                   "sample": f"arm_cnn.c on the host CPU, {cores} processes x {per_core} images per step (bounded sample of the batch)",
+                   "weights": "shipped weights.bin", "shifts": list(SHIFTS)},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"{total_imgs} images, one process per core, gcc -O3 (reference's own flags)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,19 +268,23 @@ def run_ours(args, weights):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ddist = dist if world > 1 else None
 
-    B = args.batch                                   # images per GPU (weak scaling)
+    B = args.batch                                   # images per GPU per step (weak scaling)
     acc = fc.CNNAccelerator(device=local)
     acc.load_weights(weights)
     acc.set_shifts(*SHIFTS)
     stream = torch.cuda.Stream(device=local)
     acc.use_stream(stream.cuda_stream)
 
-    # synthetic device-resident batch: this rank's contiguous shard of a world*B image stream
+    # Synthetic device-resident input: this rank's shard of a world*B image batch, in `nbuf` independent buffer pairs
+    # that the timed loop walks round-robin.  Together they are >= 2 GiB, far beyond the 126 MB L2, so no step finds
+    # its images (or the lines it will write) in cache.
     lo, hi = shard_range(B * world, rank, world)
+    nb = hi - lo
+    nbuf = max(2, -(-(2 << 30) // (nb * BYTES_PER_IMAGE)))
     g = torch.Generator(device="cuda")
     g.manual_seed(1234 + rank)
-    imgs = torch.randint(0, 256, (hi - lo, 128, 128), dtype=torch.uint8, device="cuda", generator=g)
-    feats = torch.empty((hi - lo, 64, 16, 16), dtype=torch.uint8, device="cuda")
+    imgs = [torch.randint(0, 256, (nb, 128, 128), dtype=torch.uint8, device="cuda", generator=g) for _ in range(nbuf)]
+    feats = [torch.empty((nb, 64, 16, 16), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     torch.cuda.synchronize()
 
     def barrier():
@@ -238,60 +293,74 @@ def run_ours(args, weights):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----------------------------------------------------------------
-    for _ in range(args.warmup):
-        acc.run_batch(imgs, out=feats, direct=args.direct)
+    for w in range(args.warmup):
+        acc.run_batch(imgs[w % nbuf], out=feats[w % nbuf], direct=args.direct)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     launches0 = acc.launch_count
     barrier()
     t_begin = time.time()
     acc.timer_start()
-    for _ in range(args.steps):
-        acc.run_batch(imgs, out=feats, direct=args.direct)
+    for st in range(args.steps):
+        acc.run_batch(imgs[st % nbuf], out=feats[st % nbuf], direct=args.direct)
     ms = acc.timer_stop()
     barrier()
     t_end = time.time()
     launches = acc.launch_count - launches0
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms = reduce_max(ms, ddist)
-    total_images = sum(gather_counts(hi - lo, ddist)) * args.steps
+    total_images = sum(gather_counts(nb, ddist)) * args.steps
     value = total_images / (ms / 1000.0)
 
     # ---- end to end through the C ABI with pinned host buffers -------------------------------------
     Be = min(B, args.e2e_batch)
     h_imgs = fc.alloc_host((Be, 128, 128), np.uint8)
     h_feats = fc.alloc_host((Be, 64, 16, 16), np.uint8)
-    h_imgs[:] = imgs[:Be].cpu().numpy()
+    h_imgs[:] = imgs[0][:Be].cpu().numpy()
     acc.use_stream(None)
     for _ in range(max(1, min(args.warmup, 3))):
         acc.run_batch(h_imgs, out=h_feats, direct=args.direct)
-    e2e_steps = max(1, min(args.steps, 10))
+    e2e_steps = max(1, args.steps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         acc.run_batch(h_imgs, out=h_feats, direct=args.direct)       # synchronous: returns when feats are on the host
     e2e_s = reduce_max(time.perf_counter() - t0, ddist)
     e2e_value = world * Be * e2e_steps / e2e_s
-    ok = bool(np.array_equal(h_feats[:64], feats[:64].cpu().numpy()))
+    acc.use_stream(stream.cuda_stream)
+    acc.run_batch(imgs[0], out=feats[0], direct=args.direct)
+    acc.synchronize()
+    ok = bool(np.array_equal(h_feats[:64], feats[0][:64].cpu().numpy()))
 
-    # ---- secondary measurements (rank 0 only, N = 1): full pipeline, batch-1 latency ---------------
+    # ---- secondary measurements (rank 0 only, N = 1): north_star batch, full pipeline, batch-1 latency ----
     extra = {}
     if world == 1 and not args.quick:
         import inputs
-        fw, fb = inputs.make_fc()
-        acc.load_classifier(fw, fb)
-        acc.use_stream(stream.cuda_stream)
-        m = min(B, 65536)
-        for _ in range(2):
-            acc.infer_batch(imgs[:m], direct=args.direct)
+        del imgs[2:], feats[2:]
+        torch.cuda.empty_cache()
+        big = 65536
+        bi = [torch.randint(0, 256, (big, 128, 128), dtype=torch.uint8, device="cuda", generator=g) for _ in range(2)]
+        bf = [torch.empty((big, 64, 16, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        for i in range(3):
+            acc.run_batch(bi[i % 2], out=bf[i % 2], direct=args.direct)
         torch.cuda.synchronize()
         acc.timer_start()
-        for _ in range(3):
-            acc.infer_batch(imgs[:m], direct=args.direct)
-        extra["full_pipeline_images_per_s"] = 3 * m / (acc.timer_stop() / 1000.0)
+        for i in range(6):
+            acc.run_batch(bi[i % 2], out=bf[i % 2], direct=args.direct)
+        extra["conv_stack_batch65536_images_per_s"] = 6 * big / (acc.timer_stop() / 1000.0)      # the north_star's target condition
+        fw, fb = inputs.make_fc()
+        acc.load_classifier(fw, fb)
+        for i in range(2):
+            acc.infer_batch(bi[i % 2], direct=args.direct)
+        torch.cuda.synchronize()
+        acc.timer_start()
+        for i in range(4):
+            acc.infer_batch(bi[i % 2], direct=args.direct)
+        extra["full_pipeline_batch65536_images_per_s"] = 4 * big / (acc.timer_stop() / 1000.0)   # configs[2]
+        del bi, bf
         acc.use_stream(None)
         one = h_imgs[0].copy()
         lat = []
@@ -309,14 +378,15 @@ def run_ours(args, weights):
     # launch duration is ms / steps, measured with CUDA events on the launching stream.
     kernel_ms = ms / args.steps
     int8_peak = 2.0 * peaks["bf16_tflops"]
-    achieved_tops = (hi - lo) * OPS_PER_IMAGE / (kernel_ms / 1e3) / 1e12
+    achieved_tops = nb * OPS_PER_IMAGE / (kernel_ms / 1e3) / 1e12
     roofline = {
         "bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TOP/s", "frac": achieved_tops / int8_peak,
-        "traffic": None if args.direct else (hi - lo) * NCU_DRAM_BYTES_PER_IMAGE,
+        "traffic": None if args.direct else nb * NCU_DRAM_BYTES_PER_IMAGE,
         "traffic_note": "ncu dram bytes per image (profiles/r1_fused_v7_ncu_summary.txt) x images per launch",
         "peak_note": f"int8 dense peak taken as 2 x {peaks['source']} bf16 burst ({peaks['bf16_tflops']} TF/s); nominal 4500 TOP/s",
-        "algorithmic_ops_per_launch": (hi - lo) * OPS_PER_IMAGE,
-        "hbm_achieved_gbs": (hi - lo) * BYTES_PER_IMAGE / (kernel_ms / 1e3) / 1e9,
+        "algorithmic_ops_per_launch": nb * OPS_PER_IMAGE,
+        "algorithmic_bytes_per_launch": nb * BYTES_PER_IMAGE,
+        "hbm_achieved_gbs": nb * BYTES_PER_IMAGE / (kernel_ms / 1e3) / 1e9,
         "hbm_peak_gbs": peaks["hbm_gbs"],
         "kernel_ms": kernel_ms,
     }
@@ -332,10 +402,12 @@ def run_ours(args, weights):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8*s8->s32", "data": "synthetic",
-            "config": {"workload": f"conv_stack_128x128_batch{B}_per_gpu (configs[1] stack at the north_star batch)",
+            "config": {"workload": f"configs[1]: 3-layer int8 conv stack, batch {B} synthetic 128x128 images per GPU per step, "
+                                   "bit-exact vs arm_cnn.c",
                        "batch_per_gpu": B, "weights": "shipped weights.bin", "shifts": list(SHIFTS),
                        "kernel_path": "direct per-layer" if args.direct else "fused",
-                       "l2_policy": "inputs larger than L2 (in+out = %d MiB per step)" % ((hi - lo) * BYTES_PER_IMAGE >> 20),
+                       "l2_policy": "inputs larger than L2: %d buffer pairs walked round-robin, %d MiB in+out in total"
+                                    % (nbuf, nbuf * nb * BYTES_PER_IMAGE >> 20),
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": Be * 16384, "d2h_bytes_per_step": Be * 16384,
@@ -353,10 +425,10 @@ def run_ours(args, weights):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=65536, help="images per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=32768)
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step (BASELINE.json configs[1])")
+    ap.add_argument("--e2e-batch", type=int, default=4096)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--direct", action="store_true", help="time the generic per-layer kernels instead of the fused one")
     ap.add_argument("--quick", action="store_true", help="skip the secondary measurements")

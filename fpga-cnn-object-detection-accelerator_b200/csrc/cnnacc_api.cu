@@ -343,10 +343,12 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
 
     // host pointers: 3-slot pipeline, slot streams overlap H2D / kernels / D2H
     CU(h, cudaStreamSynchronize(h->stream));
-    // chunk = what one slot stages: small enough that the un-overlapped first H2D / last D2H are a small part of the
-    // call, large enough to fill the GPU (CNNACC_HOST_CHUNK_MB overrides the 32 MiB default for tuning; measured 4..64 MiB: tools/e2e_sweep.py)
-    static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 32); }();
-    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (chunk_mb << 20) / in_sz)));
+    // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
+    // chunks; each chunk costs ~35 us of launch / copy set-up, so they should not be small either: a quarter of the call,
+    // clamped to 4..32 MiB (measured 4..64 MiB on 512 MiB calls: tools/e2e_sweep.py; CNNACC_HOST_CHUNK_MB overrides).
+    static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
+    size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
     if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
     int64_t ci = 0;
     for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
