@@ -85,8 +85,14 @@ constexpr int kTraceMax = 200, kTraceRoles = 4;
         }                                                                                                          \
     } while (0)
 #define TRACE_END(role) do { if (blockIdx.x == 0 && lane == 0) trace_cnt[role] = trace_n; } while (0)
+#if CNNACC_TRACE >= 2
+#define TRACE2(role, code) TRACE(role, code)             // per-tile detail (perturbs the MMA warp noticeably)
+#else
+#define TRACE2(role, code) do { } while (0)
+#endif
 #else
 #define TRACE(role, code) do { } while (0)
+#define TRACE2(role, code) do { } while (0)
 #define TRACE_END(role) do { } while (0)
 #endif
 
@@ -427,10 +433,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int t = 0; t < 8; t++) {
                 const int h = t & 1, i0 = (t >> 2) * 16, j0 = (t & 3) * 8;
-                if (e == 0) TRACE(1, 10 + t);
+                if (e == 0) TRACE2(1, 10 + t);
                 wait_or_flag(bar(kBarTmFull0 + h), (h ? use1 : use0) & 1, kErrMmaTimeout);
                 if (h) use1++; else use0++;
-                if (e == 0) TRACE(1, 20 + t);
+                if (e == 0) TRACE2(1, 20 + t);
                 tc_fence_after();
                 const int i = i0 + (L >> 3), j = j0 + (L & 7);
 #pragma unroll
@@ -485,10 +491,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
                 const int h = s, j0 = s * 8;
-                if (e == 0) TRACE(1, 40 + s);
+                if (e == 0) TRACE2(1, 40 + s);
                 wait_or_flag(bar(kBarTmFull0 + h), (h ? use1 : use0) & 1, kErrMmaTimeout);
                 if (h) use1++; else use0++;
-                if (e == 0) TRACE(1, 50 + s);
+                if (e == 0) TRACE2(1, 50 + s);
                 tc_fence_after();
                 const int i = L >> 3, j = j0 + (L & 7);
 #pragma unroll
@@ -548,9 +554,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #pragma unroll 1
             for (int t = 0; t < 8; t++) {
                 const int h = t & 1, ty = t >> 2, tx = t & 3;
-                TRACE(0, 10 + t);
-                if (t == 0) wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout);
+                TRACE2(0, 10 + t);
+                if (t == 0) { TRACE(0, 1); wait_or_flag(bar(kBarA1TopReady), (uint32_t)k & 1, kErrAct1Timeout); TRACE(0, 2); }
                 if (t == 4) {
+                    TRACE(0, 3);
                     wait_or_flag(bar(kBarA1BotReady), (uint32_t)k & 1, kErrAct1Timeout);
                     if (k + 2 < n_local) {               // layer 0 is done with image k: refill its slot with image k+2
                         const int slot = k & 1;
@@ -562,11 +569,12 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                         }
                         __syncwarp();
                     }
+                    TRACE(0, 4);
                 }
-                TRACE(0, 20 + t);
+                TRACE2(0, 20 + t);
                 wait_or_flag(bar(kBarTmEmpty0 + h), ((h ? use1 : use0) & 1) ^ 1, kErrEmptyTimeout);   // previous use drained
                 if (h) use1++; else use0++;
-                TRACE(0, 30 + t);
+                TRACE2(0, 30 + t);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tm + h * 256;
