@@ -10,7 +10,11 @@
 #include <vector>
 
 #include "conv_direct.cuh"
+#ifdef CNNACC_EXPERIMENT_V8            // tools/experiments: all three layers on tcgen05, two issuer warps (not the product)
+#include "../../tools/experiments/conv_fused_v8.cuh"
+#else
 #include "conv_fused.cuh"
+#endif
 #include "tail.cuh"
 #include "tiling.cuh"
 #include "weights_pack.h"
@@ -302,7 +306,12 @@ int cnnacc_set_shifts(cnnacc_handle* h, int s0, int s1, int s2) {
 int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint32_t* w0, uint8_t* b1, uint8_t* b2) {
     if (!weights_bin || !w0 || !b1 || !b2 || n != CNNACC_WEIGHT_BYTES) return CNNACC_ERR_ARG;
     static_assert(CNNACC_PACK_B1_BYTES == kB1Bytes && CNNACC_PACK_B2_BYTES == kB2Bytes, "header out of date");
+#ifdef CNNACC_EXPERIMENT_V8
+    (void)w0;
+    return CNNACC_ERR_STATE;                              // the experiment packs a different layer-0 operand
+#else
     fused_pack_weights(weights_bin, reinterpret_cast<uint32_t(*)[6]>(w0), reinterpret_cast<uint32_t(*)[32]>(w0 + 96), b1, b2);
+#endif
     return CNNACC_OK;
 }
 
