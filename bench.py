@@ -34,9 +34,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 OPS_PER_IMAGE = 2 * 40_108_032          # 2 x MACs, arm_benchmark.py:237 summed over the three layers
 BYTES_PER_IMAGE = 16384 + 16384         # algorithmic HBM traffic: image in + features out
 # dram__bytes_read.sum + dram__bytes_write.sum of one conv-stack launch / images in it, from the committed
-# `ncu --set full` capture profiles/r1_fused_v7_ncu_summary.txt (16384 images: 492 802 048 B).  Below the algorithmic
+# `ncu --set full` capture profiles/r1_final_ncu_summary.txt (16384 images: 493 879 552 B).  Below the algorithmic
 # 32768 B because the tail of the feature writes is still in L2 when the kernel ends.
-NCU_DRAM_BYTES_PER_IMAGE = 30078
+NCU_DRAM_BYTES_PER_IMAGE = 30144
 SHIFTS = (2, 4, 6)
 METRIC = "images/s, bit-exact int8 conv stack (128x128 -> 64x16x16)"
 
@@ -382,7 +382,7 @@ def run_ours(args, weights):
     roofline = {
         "bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TOP/s", "frac": achieved_tops / int8_peak,
         "traffic": None if args.direct else nb * NCU_DRAM_BYTES_PER_IMAGE,
-        "traffic_note": "ncu dram bytes per image (profiles/r1_fused_v7_ncu_summary.txt) x images per launch",
+        "traffic_note": "ncu dram bytes per image (profiles/r1_final_ncu_summary.txt) x images per launch",
         "peak_note": f"int8 dense peak taken as 2 x {peaks['source']} bf16 burst ({peaks['bf16_tflops']} TF/s); nominal 4500 TOP/s",
         "algorithmic_ops_per_launch": nb * OPS_PER_IMAGE,
         "algorithmic_bytes_per_launch": nb * BYTES_PER_IMAGE,
