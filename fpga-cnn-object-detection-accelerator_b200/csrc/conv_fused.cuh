@@ -18,9 +18,10 @@
 // a block of 16 row-pairs x 8 column-pairs.
 //   layer 1: one MMA row = one 2x2 POOLING WINDOW.  N = 128 = 4 window members x 32 out-channels, and the B
 //            operand is the 3x3 kernel Toeplitz-expanded over the window's 4x4 input patch: 8 K-slabs of
-//            (2 adjacent pixels x 16 ch), LBO = parity-plane stride.  8 MMAs per 128 windows (56 % of the MAC
-//            slots are useful, but an i8 MMA costs the same ~77 clk for any N <= 128 -- profiles/
-//            r1_probe_umma_dp4a_tmem.txt -- so this is 2.5x fewer tensor cycles than N = 32 per tap pair).
+//            (2 adjacent pixels x 16 ch), LBO = parity-plane stride.  8 MMAs per 128 windows: 56 % of the MAC
+//            slots are useful, but an M=128, K=32 i8 MMA from shared memory costs max(N/2, 32 + N/4) clk
+//            (profiles/r1_probe_umma_rate.txt: N=32 -> 40, N=128 -> 64), so 64 x 64 = 4.1 k clk per image beats
+//            the 160 x 40 = 6.4 k of one N=32 MMA per tap pair.
 //            All four members of a window land in one TMEM lane: the pool is thread-local.
 //   layer 2: one MMA row = one output pixel of ONE parity (y%2, x%2); K=32 = one tap over both 16-channel
 //            planes (LBO = plane stride), 9 MMAs, N = 64; the four parities go to four TMEM column groups.
