@@ -207,6 +207,16 @@ def _ref_worker(args):
     return done, time.perf_counter() - t0, kind
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_rate(weights, cores, seconds=None, images_per_core=None):
     """images/s of the reference CPU path over `cores` processes; returns (rate, kind, images, wall_s)."""
     jobs = [(1000 + c, images_per_core or 8, weights, SHIFTS, seconds) for c in range(cores)]
@@ -243,7 +253,8 @@ def run_reference_arm(args, weights):
                    "sample": f"arm_cnn.c on the host CPU, {cores} processes x {per_core} images per step (bounded sample of the batch)",
                    "weights": "shipped weights.bin", "shifts": list(SHIFTS)},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
-                         "sample": f"{total_imgs} images, one process per core, gcc -O3 (reference's own flags)"},
+                         "sample": f"{total_imgs} images, one process per core, gcc -O3 (reference's own flags)",
+                         "cpu_model": _cpu_model()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -396,8 +407,11 @@ def run_ours(args, weights):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, kind, n_img, wall = cpu_reference_rate(weights, cores, seconds=2.0)
+            rate1, _, n1, _ = cpu_reference_rate(weights, 1, seconds=1.0)
             cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
-                   "sample": f"{n_img} images of the same workload in a 2 s window, one process per core, gcc -O3"}
+                   "sample": f"{n_img} images of the same workload in a 2 s window, one process per core, gcc -O3",
+                   "single_core_images_per_s": rate1, "single_core_ms_per_image": 1000.0 / rate1 if rate1 else None,
+                   "cpu_model": _cpu_model()}
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
