@@ -7,7 +7,6 @@
 #include <cstring>
 #include <mutex>
 #include <string>
-#include <vector>
 
 #include "conv_direct.cuh"
 #ifdef CNNACC_EXPERIMENT_V8            // tools/experiments: all three layers on tcgen05, two issuer warps (not the product)
@@ -23,11 +22,11 @@ using namespace cnnacc;
 
 namespace {
 
-constexpr int kSlots = 3;                       // H2D / compute / D2H overlap for host-pointer batches
+constexpr int kSlots = 4;                       // staging buffers in flight for host-pointer batches
 constexpr size_t kBramBytes = 16 * 4096 + 32 * 1024 + 64 * 256;   // 112-channel feature-BRAM mirror
 
 struct Slot {
-    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // H2D landed / kernels done / D2H drained
     uint8_t *d_in = nullptr, *d_out = nullptr;
     float* d_probs = nullptr; int32_t* d_cls = nullptr; int32_t* d_bbox = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_pred = 0;
@@ -40,6 +39,7 @@ std::string g_create_error;
 struct cnnacc_handle {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr;   // one stream per engine for host-pointer batches
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_done = nullptr;
     int sm_count = 0;
     bool weights_loaded = false, fc_loaded = false;
@@ -237,8 +237,12 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     cudaEvent_t* evs[] = {&h->ev_t0, &h->ev_t1, &h->ev_a, &h->ev_b, &h->ev_c, &h->ev_done};
     for (auto ev : evs)
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail("cudaEventCreate", e);
-    for (auto& s : h->slots)
-        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& s : h->slots) {
+        for (auto ev : {&s.ev_in, &s.ev_k, &s.ev_out})
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    for (auto st : {&h->st_h2d, &h->st_k, &h->st_d2h})
+        if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaHostAlloc(&h->h_img, CNNACC_IMG * CNNACC_IMG, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer(&h->h_img_dev, h->h_img, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
@@ -255,8 +259,9 @@ int cnnacc_destroy(cnnacc_handle* h) {
     cudaDeviceSynchronize();
     for (auto& s : h->slots) {
         cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_probs); cudaFree(s.d_cls); cudaFree(s.d_bbox);
-        if (s.stream) cudaStreamDestroy(s.stream);
+        for (auto ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     }
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) if (st) cudaStreamDestroy(st);
     cudaFree(h->d_wdirect); cudaFree(h->d_fcw); cudaFree(h->d_fcb);
     cudaFree(h->d_l0); cudaFree(h->d_l1); cudaFree(h->d_feat); cudaFree(h->d_img1); cudaFree(h->d_bram);
     fused_free(h->fused);
@@ -350,11 +355,15 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
         return CNNACC_OK;
     }
 
-    // host pointers: 3-slot pipeline, slot streams overlap H2D / kernels / D2H
+    // host pointers: a ring of kSlots staging buffers driven through one stream per engine (H2D copies, kernels, D2H copies),
+    // chained by per-slot events, so copies in both directions and the kernels overlap.  (One stream per slot measured the
+    // same or slightly worse; more than 4 slots made no difference: profiles/r1_e2e_chunk_sweep.txt.)
     CU(h, cudaStreamSynchronize(h->stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));   // idle unless an earlier call failed midway
     // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
-    // chunks; each chunk costs ~35 us of launch / copy set-up, so they should not be small either: a quarter of the call,
-    // clamped to 4..32 MiB (measured 4..64 MiB on 512 MiB calls: tools/e2e_sweep.py; CNNACC_HOST_CHUNK_MB overrides).
+    // chunks; each chunk costs ~20-40 us of cross-engine hand-offs on top of its copies (tools/probe_pipeline.cu shows
+    // the same for any H2D -> kernel -> D2H chain), so they should not be small either: a quarter of the call, clamped
+    // to 4..32 MiB (tools/e2e_chunk_sweep.sh; CNNACC_HOST_CHUNK_MB overrides).
     static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
     size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
@@ -364,13 +373,17 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
         const int64_t m = std::min(hchunk, n - i0);
         Slot& s = h->slots[ci % kSlots];
         if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
-        if (maps && ci > 0) CU(h, cudaStreamWaitEvent(s.stream, h->ev_c, 0));   // shared l0/l1 workspace: serialise compute
-        CU(h, cudaMemcpyAsync(s.d_in, imgs + i0 * in_sz, m * in_sz, cudaMemcpyHostToDevice, s.stream));
-        if ((rc = conv_stack_device(h, s.stream, s.d_in, m, H, W, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
-        if (maps) CU(h, cudaEventRecord(h->ev_c, s.stream));
-        CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, s.stream));
+        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));       // slot drained (its kernels ended earlier)
+        CU(h, cudaMemcpyAsync(s.d_in, imgs + i0 * in_sz, m * in_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, H, W, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
-    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    CU(h, cudaStreamSynchronize(h->st_d2h));            // the last D2H is the last operation of the whole chain
     return check_fused_status(h);
 }
 
@@ -539,28 +552,33 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     }
 
     CU(h, cudaStreamSynchronize(h->stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
     const int64_t hchunk = std::min<int64_t>(n, 4096);
     if (maps && (rc = ensure_maps(h, hchunk, CNNACC_IMG, CNNACC_IMG))) return rc;
     int64_t ci = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
         const int64_t m = std::min(hchunk, n - i0);
         Slot& s = h->slots[ci % kSlots];
         if ((rc = slot_reserve(h, s, hchunk * img_sz, src_is_images ? hchunk * img_sz : 0, hchunk))) return rc;
-        if (maps && ci > 0) CU(h, cudaStreamWaitEvent(s.stream, h->ev_c, 0));
-        CU(h, cudaMemcpyAsync(s.d_in, src + i0 * img_sz, m * img_sz, cudaMemcpyHostToDevice, s.stream));
+        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, src + i0 * img_sz, m * img_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        if (cls_given) CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
         const uint8_t* f = s.d_in;
         if (src_is_images) {
-            if ((rc = conv_stack_device(h, s.stream, s.d_in, m, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
-            if (maps) CU(h, cudaEventRecord(h->ev_c, s.stream));
+            if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
             f = s.d_out;
         }
-        if (cls_given) CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, s.stream));
-        if ((rc = launch_tail(h, s.stream, f, m, s.d_probs, s.d_cls, s.d_bbox, cls_given))) return rc;
-        if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-        if (cls && !cls_given) CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if ((rc = launch_tail(h, h->st_k, f, m, s.d_probs, s.d_cls, s.d_bbox, cls_given))) return rc;
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
+        if (cls && !cls_given) CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+        if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
-    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    CU(h, cudaStreamSynchronize(h->st_d2h));
     return CNNACC_OK;
 }
 
@@ -604,7 +622,7 @@ int cnnacc_synchronize(cnnacc_handle* h) {
     if (!h) return CNNACC_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
-    for (auto& s : h->slots) CU(h, cudaStreamSynchronize(s.stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
     return check_fused_status(h);
 }
 
