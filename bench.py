@@ -228,6 +228,20 @@ def cpu_reference_rate(weights, cores, seconds=None, images_per_core=None):
     return rate, res[0][2], sum(d for d, _, _ in res), wall
 
 
+def numpy_port_ms(weights, reps=3):
+    """ms per image of the numpy restatement (oracle/np_oracle.py), the reference's own slow path
+    (dump_arm_features.numpy_infer); reported once beside the C rate, median of `reps`."""
+    from oracle import np_oracle
+    kern = np_oracle.unpack_weights(weights)
+    img = np.random.default_rng(7).integers(0, 256, (128, 128), dtype=np.uint8)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        np_oracle.infer(img, kern, tuple(SHIFTS))
+        ts.append(time.perf_counter() - t0)
+    return 1000.0 * sorted(ts)[len(ts) // 2]
+
+
 def run_reference_arm(args, weights):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -411,7 +425,7 @@ def run_ours(args, weights):
             cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
                    "sample": f"{n_img} images of the same workload in a 2 s window, one process per core, gcc -O3",
                    "single_core_images_per_s": rate1, "single_core_ms_per_image": 1000.0 / rate1 if rate1 else None,
-                   "cpu_model": _cpu_model()}
+                   "numpy_port_ms_per_image": numpy_port_ms(weights), "cpu_model": _cpu_model()}
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
