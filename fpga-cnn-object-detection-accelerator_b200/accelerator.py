@@ -201,8 +201,10 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_load_classifier(self._h, _vp(fc_w), _vp(fc_b), fc_w.shape[0]))
         self._n_cls = fc_w.shape[0]
 
-    def _predict(self, fn, x, direct=False):
-        flags = _lib.FLAG_DIRECT if direct else 0
+    def _predict(self, fn, x, direct=False, bbox="vec"):
+        if bbox not in ("vec", "upsampled"):
+            raise ValueError("bbox must be 'vec' (realtime_detect.bbox_vec) or 'upsampled' (Classifier.get_cam_bbox)")
+        flags = (_lib.FLAG_DIRECT if direct else 0) | (_lib.FLAG_BBOX_UPSAMPLED if bbox == "upsampled" else 0)
         if self._n_cls == 0:
             raise RuntimeError("classifier not loaded")
         if _is_torch_cuda(x):
@@ -225,9 +227,25 @@ class CNNAccelerator:
         self._check(fn(self._h, _vp(x), n, _vp(probs), _vp(cls), _vp(bbox), flags))
         return cls, probs, bbox
 
-    def classify_batch(self, features):
-        """features [N,64,256] (or [N,64,16,16]) u8 -> (cls [N] i32, probs [N,n_cls] f32, bbox [N,4] i32)."""
-        return self._predict(self._libc.cnnacc_classify_batch, features)
+    def classify_batch(self, features, bbox="vec"):
+        """features [N,64,256] (or [N,64,16,16]) u8 -> (cls [N] i32, probs [N,n_cls] f32, bbox [N,4] i32).
+        bbox='vec': realtime_detect.bbox_vec; bbox='upsampled': pynq_inference.Classifier.get_cam_bbox."""
+        return self._predict(self._libc.cnnacc_classify_batch, features, bbox=bbox)
+
+    def cam_bbox_batch(self, features, cls, return_cam=False):
+        """Classifier.get_cam_bbox (pynq_inference.py:349-408) for given classes: features [N,64,256] u8 + cls [N] i32
+        -> bbox [N,4] i32 (x1,y1,x2,y2), and with return_cam the upsampled maps [N,128,128] u8 (cam_full = maps/255)."""
+        if self._n_cls == 0:
+            raise RuntimeError("classifier not loaded")
+        x = np.ascontiguousarray(features, dtype=np.uint8)
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        n = x.shape[0]
+        if x[0].size != 16384 or cls.shape != (n,):
+            raise ValueError("expected [N,64,256] features and [N] classes")
+        bbox = np.empty((n, 4), dtype=np.int32)
+        cam = np.empty((n, 128, 128), dtype=np.uint8) if return_cam else None
+        self._check(self._libc.cnnacc_cam_bbox_batch(self._h, _vp(x), n, _vp(cls), _vp(bbox), _vp(cam) if return_cam else None, 0))
+        return (bbox, cam) if return_cam else bbox
 
     def bbox_batch(self, features, cls):
         """bbox_vec for given classes: features [N,64,256] u8 + cls [N] i32 -> bbox [N,4] i32 (host arrays)."""
@@ -242,9 +260,9 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_classify_batch(self._h, _vp(x), n, None, _vp(cls), _vp(bbox), _lib.FLAG_CLS_GIVEN))
         return bbox
 
-    def infer_batch(self, images, direct=False):
+    def infer_batch(self, images, direct=False, bbox="vec"):
         """images [N,128,128] u8 -> (cls, probs, bbox); features never leave the GPU."""
-        return self._predict(self._libc.cnnacc_infer_batch, images, direct)
+        return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox)
 
     def infer_one(self, gray128):
         """One image, lowest latency.  -> (feat (64,256) u8, conv_ms, read_ms)."""
@@ -301,7 +319,8 @@ class ARMEngine:
 
 
 class Classifier:
-    """pynq_inference.py:292-347 on the GPU: classify((64,256) u8) -> (class_index, class_name, confidence, probabilities).
+    """pynq_inference.py:292-408 on the GPU: classify((64,256) u8) -> (class_index, class_name, confidence, probabilities)
+    and get_cam_bbox(features, class_idx) -> (cam_full, (x1, y1, x2, y2)).
 
     The reference takes the exact-integer bin mean and then divides by 255; the tail kernel computes S/4080 in one
     rounding, which is the same fp32 value.  Weights must be (num_classes, 1024) -- the (6,64) GAP file the reference
@@ -325,6 +344,14 @@ class Classifier:
         idx = int(cls[0])
         name = self.class_names[idx] if self.class_names else str(idx)
         return idx, name, float(probs[0, idx]), probs[0]
+
+    def get_cam_bbox(self, features, class_idx, img_size=128):
+        """pynq_inference.py:349-408 -> (cam_full (128,128) f32 in 0..1, (x1, y1, x2, y2))."""
+        if img_size != 128:
+            raise ValueError("img_size is 128 (IMG_SIZE, pynq_inference.py:72)")
+        bbox, cam = self._acc.cam_bbox_batch(np.asarray(features, dtype=np.uint8).reshape(1, 64, 256),
+                                             np.array([class_idx], dtype=np.int32), return_cam=True)
+        return cam[0].astype(np.float32) / 255.0, tuple(int(v) for v in bbox[0])
 
 
 def dump_features(acc, images, labels, names, output, shifts=None):

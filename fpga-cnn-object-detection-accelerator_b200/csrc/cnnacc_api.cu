@@ -15,6 +15,7 @@
 #include "conv_fused.cuh"
 #endif
 #include "tail.cuh"
+#include "cam_upsampled.cuh"
 #include "tiling.cuh"
 #include "weights_pack.h"
 
@@ -165,6 +166,17 @@ int launch_tail(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, i
     if (n == 0) return 0;
     classify_bbox_kernel<<<(unsigned)n, 256, 0, stream>>>(d_feats, h->d_fcw, h->d_fcb, h->n_cls, d_probs, d_cls, d_bbox,
                                                           cls_given ? d_cls : nullptr);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
+// Classifier.get_cam_bbox per image (cam_upsampled.cuh); d_cam may be null
+int launch_cam_upsampled(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, int64_t n, const int32_t* d_cls,
+                         int32_t* d_bbox, uint8_t* d_cam) {
+    if (n == 0) return 0;
+    static const ResampleTab tab = make_resample_tab();
+    cam_bbox_upsampled_kernel<<<(unsigned)n, 256, 0, stream>>>(d_feats, h->d_fcw, h->n_cls, d_cls, d_bbox, d_cam, tab);
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -531,6 +543,9 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     const bool maps = src_is_images && needs_maps(h, CNNACC_IMG, CNNACC_IMG, flags);
     const bool cls_given = (flags & CNNACC_FLAG_CLS_GIVEN) != 0;
     if (cls_given && !cls) return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_CLS_GIVEN without a cls array");
+    const bool upsampled = (flags & CNNACC_FLAG_BBOX_UPSAMPLED) != 0;
+    if (upsampled && bbox && !cls && (flags & CNNACC_FLAG_DEVICE_PTRS))
+        return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_BBOX_UPSAMPLED with device pointers needs a cls array");
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
         const int64_t chunk = std::min<int64_t>(n, 16384);
@@ -546,7 +561,8 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
                 f = h->d_feat;
             }
             if ((rc = launch_tail(h, h->stream, f, m, probs ? probs + i0 * nc : nullptr, cls ? cls + i0 : nullptr,
-                                  bbox ? bbox + i0 * 4 : nullptr, cls_given))) return rc;
+                                  (bbox && !upsampled) ? bbox + i0 * 4 : nullptr, cls_given))) return rc;
+            if (bbox && upsampled && (rc = launch_cam_upsampled(h, h->stream, f, m, cls + i0, bbox + i0 * 4, nullptr))) return rc;
         }
         return CNNACC_OK;
     }
@@ -570,7 +586,8 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
             if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
             f = s.d_out;
         }
-        if ((rc = launch_tail(h, h->st_k, f, m, s.d_probs, s.d_cls, s.d_bbox, cls_given))) return rc;
+        if ((rc = launch_tail(h, h->st_k, f, m, s.d_probs, s.d_cls, upsampled ? nullptr : s.d_bbox, cls_given))) return rc;
+        if (bbox && upsampled && (rc = launch_cam_upsampled(h, h->st_k, f, m, s.d_cls, s.d_bbox, nullptr))) return rc;
         CU(h, cudaEventRecord(s.ev_k, h->st_k));
         CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
         if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
@@ -588,6 +605,42 @@ int cnnacc_classify_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, flo
 
 int cnnacc_infer_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
     return predict_impl(h, imgs, n, true, probs, cls, bbox, flags);
+}
+
+int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, const int32_t* cls, int32_t* bbox, uint8_t* cam,
+                          uint32_t flags) {
+    int rc;
+    if (!h) return CNNACC_ERR_ARG;
+    if (!h->fc_loaded) return fail(h, CNNACC_ERR_STATE, "classifier not loaded (call cnnacc_load_classifier)");
+    if (n < 0) return fail(h, CNNACC_ERR_ARG, "negative n");
+    if (n == 0) return CNNACC_OK;
+    if (!feats || !cls || (!bbox && !cam)) return fail(h, CNNACC_ERR_ARG, "NULL feature / class pointer, or nothing to write");
+    CU(h, cudaSetDevice(h->device));
+    const size_t feat_sz = CNNACC_FEAT_BYTES, cam_sz = (size_t)kCamOut * kCamOut;
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) return launch_cam_upsampled(h, h->stream, feats, n, cls, bbox, cam);
+
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    const int64_t hchunk = std::min<int64_t>(n, 4096);
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
+        const int64_t m = std::min(hchunk, n - i0);
+        Slot& s = h->slots[ci % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * feat_sz, cam ? hchunk * cam_sz : 0, hchunk))) return rc;
+        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, feats + i0 * feat_sz, m * feat_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        if ((rc = launch_cam_upsampled(h, h->st_k, s.d_in, m, s.d_cls, bbox ? s.d_bbox : nullptr, cam ? s.d_out : nullptr))) return rc;
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        if (bbox) CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+        if (cam)  CU(h, cudaMemcpyAsync(cam + i0 * cam_sz, s.d_out, m * cam_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+    }
+    CU(h, cudaStreamSynchronize(h->st_d2h));
+    return CNNACC_OK;
 }
 
 int cnnacc_alloc_host(size_t bytes, void** out) {

@@ -45,6 +45,8 @@ extern "C" {
 #define CNNACC_FLAG_DIRECT        0x2u  /* use the generic per-layer kernels even for 128x128 (cross-check path) */
 #define CNNACC_FLAG_KEEP_MAPS     0x4u  /* keep image 0's layer-0/1 maps for cnnacc_read_feature_map (BRAM ch 0-47) */
 #define CNNACC_FLAG_CLS_GIVEN     0x8u  /* classify_batch: cls[] is an INPUT (bbox_vec's cls_idx argument), not written */
+#define CNNACC_FLAG_BBOX_UPSAMPLED 0x10u /* classify_batch / infer_batch: bbox = Classifier.get_cam_bbox (pynq_inference.py:349-408:
+                                            u8 CAM -> PIL bilinear 16->128 -> percentile / 0.2 floor -> pad 3) instead of bbox_vec */
 
 typedef struct cnnacc_handle cnnacc_handle;
 
@@ -124,6 +126,12 @@ int cnnacc_classify_batch(cnnacc_handle *h, const uint8_t *feats, int64_t n,
                           float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
 int cnnacc_infer_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n,
                        float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
+/* cam_bbox_batch : Classifier.get_cam_bbox(features, class_idx, img_size=128) (pynq_inference.py:349-408) per image:
+ *                  feats [n][64][256] u8, cls [n] i32 (the class_idx argument) -> bbox [n][4] i32 (x1,y1,x2,y2) and,
+ *                  when cam != NULL, cam [n][128][128] u8 = the upsampled map (the reference's cam_full is cam/255 as f32).
+ *                  Pillow's BILINEAR resize of an 8-bit image is integer arithmetic and is reproduced bit for bit. */
+int cnnacc_cam_bbox_batch(cnnacc_handle *h, const uint8_t *feats, int64_t n, const int32_t *cls,
+                          int32_t *bbox, uint8_t *cam, uint32_t flags);
 
 /* ---- host memory the DMA engines can stream from (pynq.allocate, realtime_detect.py:293,301) */
 int cnnacc_alloc_host(size_t bytes, void **out);

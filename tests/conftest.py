@@ -31,3 +31,8 @@ def conv_golden():
 @pytest.fixture(scope="session")
 def tail_golden():
     return np.load(os.path.join(GOLDEN, "tail_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def cam_golden():
+    return np.load(os.path.join(GOLDEN, "cam_cases.npz"))

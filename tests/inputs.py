@@ -103,3 +103,49 @@ HW_CASES = [
     dict(name="hw_64x32", weights=("rng", 21), images=("rng", 22), H=64, W=32, shifts=(9, 12, 13)),
     dict(name="hw_512x512", weights="shipped", images=("smooth", 23), H=512, W=512, shifts=(6, 9, 10)),
 ]
+
+
+def make_features(kind, n):
+    """Synthetic (n,64,256) u8 feature maps for the classifier / CAM tail.
+    kind: ('rng', seed) full range | ('low', seed) small values | ('saturated', seed) some channels all 255 |
+          ('blob', seed) a few bright blobs on a dark map | ('sparse', seed) mostly zero | 'zeros' | 'full'."""
+    if kind == "zeros":
+        return np.zeros((n, 64, 256), dtype=np.uint8)
+    if kind == "full":
+        return np.full((n, 64, 256), 255, dtype=np.uint8)
+    tag, seed = kind
+    rng = np.random.default_rng(seed)
+    f = rng.integers(0, 256, (n, 64, 256), dtype=np.uint8)
+    if tag == "rng":
+        return f
+    if tag == "low":
+        return (f >> 4).astype(np.uint8)
+    if tag == "saturated":
+        for i in range(n):
+            f[i, rng.choice(64, size=int(rng.integers(1, 40)), replace=False)] = 255
+        return f
+    if tag == "sparse":
+        f[rng.random(f.shape) < 0.95] = 0
+        return f
+    if tag == "blob":
+        out = np.zeros((n, 64, 16, 16), dtype=np.int64)
+        yy, xx = np.mgrid[0:16, 0:16]
+        for i in range(n):
+            for _ in range(int(rng.integers(1, 4))):
+                cy, cx, r = rng.integers(0, 16), rng.integers(0, 16), rng.integers(1, 6)
+                amp = rng.integers(40, 256, 64)
+                out[i] += amp[:, None, None] * ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r)
+        return np.clip(out + (f.reshape(n, 64, 16, 16) >> 5), 0, 255).astype(np.uint8).reshape(n, 64, 256)
+    raise ValueError(kind)
+
+
+# Classifier.get_cam_bbox cases pinned by tests/golden/cam_cases.npz (tests/golden/make_cam_golden.py)
+CAM_CASES = [
+    dict(name="cam_rng", features=("rng", 40), n=6),
+    dict(name="cam_low", features=("low", 41), n=4),
+    dict(name="cam_saturated", features=("saturated", 42), n=6),
+    dict(name="cam_blob", features=("blob", 43), n=8),
+    dict(name="cam_sparse", features=("sparse", 44), n=4),
+    dict(name="cam_zeros", features="zeros", n=1),
+    dict(name="cam_full", features="full", n=1),
+]

@@ -127,3 +127,61 @@ def test_tail_oracle_matches_reference_fixtures(conv_golden, tail_golden):
             assert np.array_equal(p, tail_golden[case["name"] + "__probs"][i])
             box, _ = np_oracle.bbox_vec(feats[i], cls, fc_w)
             assert tuple(tail_golden[case["name"] + "__bbox"][i]) == box
+
+
+# ---- Classifier.get_cam_bbox (pynq_inference.py:349-408): Pillow's bilinear resize restated ----------------------
+
+def _cam_sets(conv_golden):
+    sets = [(c["name"], inputs.make_features(c["features"], c["n"])) for c in inputs.CAM_CASES]
+    for name in ("rng_shipped_mid", "smooth_shipped", "rng_random_mid"):
+        sets.append(("cam_conv_" + name, conv_golden[name][:4]))
+    return sets
+
+
+def test_pil_bilinear_restatement_matches_pillow_fixtures(cam_golden):
+    for src, dst in zip(cam_golden["pil__src"], cam_golden["pil__dst"]):
+        assert np.array_equal(np_oracle.pil_resize_bilinear_u8(src, 128), dst)
+    bounds, kk = np_oracle.pil_bilinear_coeffs(16, 128)
+    assert kk.shape == (128, 3) and all(abs(int(r.sum()) - (1 << 22)) <= 2 for r in kk)      # 22-bit fixed point, sums to 1
+    assert bounds[0] == (0, 1) and bounds[4] == (0, 2) and bounds[127] == (15, 1) and max(n for _, n in bounds) <= 3
+
+
+def test_cam_bbox_oracle_matches_reference_fixtures(conv_golden, cam_golden):
+    fc_w, _ = inputs.make_fc()
+    for name, feats in _cam_sets(conv_golden):
+        cls, box, cam = cam_golden[name + "__cls"], cam_golden[name + "__box"], cam_golden[name + "__cam"]
+        for i in range(feats.shape[0]):
+            for k in range(6):
+                cam_u8, b = np_oracle.get_cam_bbox(feats[i], k, fc_w)
+                assert b == tuple(box[i, k]), (name, i, k)
+                assert np_oracle.get_cam_bbox_levels(cam_u8) == b, (name, i, k)
+                if k == cls[i]:
+                    assert np.array_equal(cam_u8, cam[i]), (name, i)
+
+
+def test_cam_threshold_is_an_integer_level_rule():
+    """np.percentile(cam_u8/255, 70) then max(., 0.2) then '>' == level > max(level of sorted[11468], 51), also when the
+    two elements the percentile interpolates between differ, and around the 0.2 floor (51/255 == 0.2f)."""
+    rng = np.random.default_rng(3)
+
+    def float_rule(cam_u8):
+        cam_full = cam_u8.astype(np.float32) / 255.0
+        mask = cam_full > max(np.percentile(cam_full, 70), 0.2)
+        if not mask.any():
+            return (0, 0, 127, 127)
+        rows, cols = np.any(mask, 1), np.any(mask, 0)
+        y1, y2 = np.where(rows)[0][[0, -1]]
+        x1, x2 = np.where(cols)[0][[0, -1]]
+        return (int(max(0, x1 - 3)), int(max(0, y1 - 3)), int(min(127, x2 + 3)), int(min(127, y2 + 3)))
+
+    cams = []
+    for _ in range(150):
+        a, b = sorted(rng.integers(0, 256, 2))
+        n_a = 11469 + int(rng.integers(-1, 2))
+        cams.append(np.concatenate([np.full(n_a, a, np.uint8), rng.integers(b, 256, 16384 - n_a).astype(np.uint8)]))
+    for a in (49, 50, 51, 52, 53):
+        for n_a in (11468, 11469, 11470):
+            cams.append(np.concatenate([np.full(n_a, a, np.uint8), rng.integers(50, 56, 16384 - n_a).astype(np.uint8)]))
+    for v in cams:
+        rng.shuffle(v)
+        assert float_rule(v.reshape(128, 128)) == np_oracle.get_cam_bbox_levels(v.reshape(128, 128))

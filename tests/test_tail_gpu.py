@@ -122,3 +122,67 @@ def test_classifier_object_and_feature_dump(tmp_path, conv_golden, shipped_weigh
     assert z["features"].shape == (8, 64, 256) and z["features"].dtype == np.uint8
     assert np.array_equal(z["features"], conv_golden["rng_shipped_mid"]) and list(z["shifts"]) == [7, 10, 11]
     assert list(z["labels"]) == list(range(8)) and list(z["names"]) == [f"img{i}" for i in range(8)]
+
+
+# ---- Classifier.get_cam_bbox (pynq_inference.py:349-408): integer outputs, must match exactly -------------------
+
+def test_cam_bbox_fixtures(acc, conv_golden, cam_golden):
+    sets = [(c["name"], inputs.make_features(c["features"], c["n"])) for c in inputs.CAM_CASES]
+    for name in ("rng_shipped_mid", "smooth_shipped", "rng_random_mid"):
+        sets.append(("cam_conv_" + name, conv_golden[name][:4]))
+    for name, feats in sets:
+        n = feats.shape[0]
+        for k in range(6):
+            box = acc.cam_bbox_batch(feats, np.full(n, k, dtype=np.int32))
+            assert np.array_equal(box, cam_golden[name + "__box"][:, k]), (name, k)
+        cls = cam_golden[name + "__cls"]
+        box, cam = acc.cam_bbox_batch(feats, cls, return_cam=True)
+        assert np.array_equal(cam, cam_golden[name + "__cam"]), name
+        assert np.array_equal(box, cam_golden[name + "__box"][np.arange(n), cls]), name
+        # the same box through the fused tail
+        cls2, _, box2 = acc.classify_batch(feats, bbox="upsampled")
+        assert np.array_equal(cls2, cls) and np.array_equal(box2, box), name
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_cam_bbox_random_features_vs_oracle(seed):
+    import fpga_cnn_b200 as fc
+    rng = np.random.default_rng(100 + seed)
+    n = 150
+    feats = np.concatenate([_random_features(rng, n - 40), inputs.make_features(("blob", 200 + seed), 40)])
+    w, b = inputs.make_fc(seed=60 + seed)
+    a = fc.CNNAccelerator()
+    a.load_classifier(w, b)
+    cls = rng.integers(0, 6, n).astype(np.int32)
+    box, cam = a.cam_bbox_batch(feats, cls, return_cam=True)
+    a.close()
+    for i in range(n):
+        cam_ref, box_ref = np_oracle.get_cam_bbox(feats[i], int(cls[i]), w)
+        assert np.array_equal(cam[i], cam_ref), i
+        assert tuple(box[i]) == box_ref, i
+
+
+def test_cam_bbox_object_surface_and_pipeline(conv_golden, cam_golden, shipped_weights):
+    import fpga_cnn_b200 as fc
+    w, b = inputs.make_fc()
+    clf = fc.Classifier(w, b)
+    feats = inputs.make_features(("blob", 43), 8)
+    for i in range(3):
+        idx = clf.classify(feats[i])[0]
+        cam_full, box = clf.get_cam_bbox(feats[i], idx)
+        assert cam_full.dtype == np.float32 and cam_full.shape == (128, 128)
+        assert np.array_equal(cam_full, cam_golden["cam_blob__cam"][i].astype(np.float32) / 255.0)
+        assert box == tuple(int(v) for v in cam_golden["cam_blob__box"][i, idx])
+    # images in, upsampled boxes out == run_batch + cam_bbox_batch
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    a.load_classifier(w, b)
+    imgs = inputs.make_images(("rng", 1), 8)
+    cls, probs, box = a.infer_batch(imgs, bbox="upsampled")
+    f = a.run_batch(imgs).reshape(8, 64, 256)
+    assert np.array_equal(f, conv_golden["rng_shipped_mid"])
+    assert np.array_equal(box, a.cam_bbox_batch(f, cls))
+    with pytest.raises(ValueError):
+        a.classify_batch(f, bbox="nope")
+    a.close()
