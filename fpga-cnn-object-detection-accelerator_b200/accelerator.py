@@ -264,6 +264,46 @@ class CNNAccelerator:
         """images [N,128,128] u8 -> (cls, probs, bbox); features never leave the GPU."""
         return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox)
 
+    def preprocess(self, frames):
+        """realtime_detect.py:582-591 for a batch: frames [N,h,w,3] u8 BGR -> [N,128,128] u8 (centre-crop, BGR2GRAY,
+        INTER_AREA), bit-identical to cv2 4.13.  numpy in -> numpy out; torch CUDA tensor in -> torch CUDA tensor out."""
+        if _is_torch_cuda(frames):
+            import torch
+            if frames.dim() != 4 or frames.shape[3] != 3 or frames.dtype != torch.uint8 or not frames.is_contiguous():
+                raise ValueError("expected a contiguous [N,h,w,3] uint8 tensor")
+            n, fh, fw = frames.shape[:3]
+            out = torch.empty((n, 128, 128), dtype=torch.uint8, device=frames.device)
+            self._check(self._libc.cnnacc_preprocess_bgr(self._h, ctypes.c_void_p(frames.data_ptr()), n, fh, fw,
+                                                         ctypes.c_void_p(out.data_ptr()), _lib.FLAG_DEVICE_PTRS))
+            return out
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("expected [N,h,w,3] BGR frames")
+        n, fh, fw = frames.shape[:3]
+        out = np.empty((n, 128, 128), dtype=np.uint8)
+        self._check(self._libc.cnnacc_preprocess_bgr(self._h, _vp(frames), n, fh, fw, _vp(out), 0))
+        return out
+
+    def detect_frames(self, frames, bbox="vec", return_gray=False):
+        """The loop body of realtime_detect.py:582-598 for a batch of camera frames [N,h,w,3] u8 BGR (host array):
+        preprocess -> conv stack -> classify -> CAM box on the GPU.  -> (cls, probs, bbox[, gray128])."""
+        if bbox not in ("vec", "upsampled"):
+            raise ValueError("bbox must be 'vec' or 'upsampled'")
+        if self._n_cls == 0:
+            raise RuntimeError("classifier not loaded")
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("expected [N,h,w,3] BGR frames")
+        n, fh, fw = frames.shape[:3]
+        probs = np.empty((n, self._n_cls), dtype=np.float32)
+        cls = np.empty((n,), dtype=np.int32)
+        box = np.empty((n, 4), dtype=np.int32)
+        gray = np.empty((n, 128, 128), dtype=np.uint8) if return_gray else None
+        self._check(self._libc.cnnacc_detect_frames(self._h, _vp(frames), n, fh, fw, _vp(gray) if return_gray else None,
+                                                    _vp(probs), _vp(cls), _vp(box),
+                                                    _lib.FLAG_BBOX_UPSAMPLED if bbox == "upsampled" else 0))
+        return (cls, probs, box, gray) if return_gray else (cls, probs, box)
+
     def infer_one(self, gray128):
         """One image, lowest latency.  -> (feat (64,256) u8, conv_ms, read_ms)."""
         img = np.ascontiguousarray(gray128, dtype=np.uint8).reshape(-1)

@@ -16,6 +16,7 @@
 #endif
 #include "tail.cuh"
 #include "cam_upsampled.cuh"
+#include "preprocess.cuh"
 #include "tiling.cuh"
 #include "weights_pack.h"
 
@@ -54,6 +55,10 @@ struct cnnacc_handle {
     uint8_t *d_l0 = nullptr, *d_l1 = nullptr, *d_feat = nullptr;
     size_t cap_l0 = 0, cap_l1 = 0, cap_feat = 0;
     Slot slots[kSlots];
+    // pre-processing (preprocess.cuh): INTER_AREA weight table of the last crop side seen
+    int prep_side = 0; AreaTabHost prep_tab;
+    int *d_prep_start = nullptr, *d_prep_cnt = nullptr; float* d_prep_alpha = nullptr; size_t cap_prep_alpha = 0;
+    uint8_t* d_gray = nullptr; size_t cap_gray = 0;
     // single-image protocol state
     uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned + mapped: the batch-1 path runs zero-copy on them
     uint8_t *h_img_dev = nullptr, *h_bram_dev = nullptr;   // their device addresses
@@ -182,6 +187,43 @@ int launch_cam_upsampled(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d
     return 0;
 }
 
+// realtime_detect.py:582-591 for n frames already on the device (preprocess.cuh)
+int launch_preprocess(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_frames, int64_t n, int fh, int fw, uint8_t* d_gray) {
+    if (n == 0) return 0;
+    const int S = std::min(fh, fw);
+    if (S != h->prep_side) {
+        CU(h, cudaDeviceSynchronize());                  // nothing in flight may still be reading the old table
+        h->prep_tab = make_area_tab(S);
+        if (!h->d_prep_start) CU(h, cudaMalloc(&h->d_prep_start, kPrepOut * sizeof(int)));
+        if (!h->d_prep_cnt) CU(h, cudaMalloc(&h->d_prep_cnt, kPrepOut * sizeof(int)));
+        const size_t ab = h->prep_tab.alpha.size() * sizeof(float);
+        if (ab > h->cap_prep_alpha) {
+            cudaFree(h->d_prep_alpha); h->d_prep_alpha = nullptr; h->cap_prep_alpha = 0;
+            CU(h, cudaMalloc(&h->d_prep_alpha, ab));
+            h->cap_prep_alpha = ab;
+        }
+        CU(h, cudaMemcpy(h->d_prep_start, h->prep_tab.start.data(), kPrepOut * sizeof(int), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_prep_cnt, h->prep_tab.cnt.data(), kPrepOut * sizeof(int), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_prep_alpha, h->prep_tab.alpha.data(), ab, cudaMemcpyHostToDevice));
+        h->prep_side = S;
+    }
+    PrepParams P;
+    P.frames = d_frames; P.out = d_gray;
+    P.start = h->d_prep_start; P.cnt = h->d_prep_cnt; P.alpha = h->d_prep_alpha;
+    P.fh = fh; P.fw = fw;
+    P.x0 = fw > fh ? (fw - fh) / 2 : 0;                  // realtime_detect.py:583-589
+    P.y0 = fh > fw ? (fh - fw) / 2 : 0;
+    P.mode = h->prep_tab.mode; P.k = h->prep_tab.k; P.taps = h->prep_tab.taps; P.inv = h->prep_tab.inv;
+    for (int64_t i0 = 0; i0 < n; i0 += 65535) {          // gridDim.y limit
+        const int64_t m = std::min<int64_t>(65535, n - i0);
+        P.frames = d_frames + (size_t)i0 * fh * fw * 3; P.out = d_gray + (size_t)i0 * kPrepOut * kPrepOut;
+        preprocess_bgr_kernel<<<dim3(kPrepOut / kPrepRowsPerCta, (unsigned)m), kPrepOut, 0, stream>>>(P);
+        h->launches++;
+    }
+    CU(h, cudaGetLastError());
+    return 0;
+}
+
 int slot_reserve(cnnacc_handle* h, Slot& s, size_t in_bytes, size_t out_bytes, size_t n_pred) {
     int rc;
     if ((rc = grow(h, &s.d_in, &s.cap_in, in_bytes))) return rc;
@@ -274,6 +316,7 @@ int cnnacc_destroy(cnnacc_handle* h) {
         for (auto ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     }
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) if (st) cudaStreamDestroy(st);
+    cudaFree(h->d_prep_start); cudaFree(h->d_prep_cnt); cudaFree(h->d_prep_alpha); cudaFree(h->d_gray);
     cudaFree(h->d_wdirect); cudaFree(h->d_fcw); cudaFree(h->d_fcb);
     cudaFree(h->d_l0); cudaFree(h->d_l1); cudaFree(h->d_feat); cudaFree(h->d_img1); cudaFree(h->d_bram);
     fused_free(h->fused);
@@ -641,6 +684,85 @@ int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, con
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
     return CNNACC_OK;
+}
+
+// shared body of preprocess_bgr (gray128 out) and detect_frames (predictions out)
+static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int fh, int fw, uint8_t* gray128,
+                       float* probs, int32_t* cls, int32_t* bbox, bool detect, uint32_t flags) {
+    int rc;
+    if (!h) return CNNACC_ERR_ARG;
+    if (detect) {
+        if ((rc = check_ready(h))) return rc;
+        if (!h->fc_loaded) return fail(h, CNNACC_ERR_STATE, "classifier not loaded (call cnnacc_load_classifier)");
+    }
+    if (n < 0 || fh < kPrepOut || fw < kPrepOut || std::min(fh, fw) > kPrepMaxSide)
+        return fail(h, CNNACC_ERR_ARG, "bad n / frame size (the square crop must be 128..8192 pixels a side)");
+    if (n == 0) return CNNACC_OK;
+    if (!frames || (!detect && !gray128)) return fail(h, CNNACC_ERR_ARG, "NULL frame / output pointer");
+    CU(h, cudaSetDevice(h->device));
+    const size_t frame_sz = (size_t)fh * fw * 3, img_sz = CNNACC_FEAT_BYTES;
+    const int nc = h->n_cls;
+    const bool upsampled = (flags & CNNACC_FLAG_BBOX_UPSAMPLED) != 0;
+    auto tail = [&](cudaStream_t st, const uint8_t* d_gray, int64_t m, float* d_probs, int32_t* d_cls, int32_t* d_bbox) -> int {
+        int r;
+        if ((r = grow(h, &h->d_feat, &h->cap_feat, (size_t)m * img_sz))) return r;
+        if ((r = conv_stack_device(h, st, d_gray, m, CNNACC_IMG, CNNACC_IMG, h->d_feat, 0, h->d_l0, h->d_l1))) return r;
+        if ((r = launch_tail(h, st, h->d_feat, m, d_probs, d_cls, upsampled ? nullptr : d_bbox))) return r;
+        if (upsampled && d_bbox && (r = launch_cam_upsampled(h, st, h->d_feat, m, d_cls, d_bbox, nullptr))) return r;
+        return 0;
+    };
+
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        if (detect && upsampled && bbox && !cls) return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_BBOX_UPSAMPLED with device pointers needs a cls array");
+        const int64_t chunk = std::min<int64_t>(n, 16384);
+        uint8_t* g = gray128;
+        if (!g) { if ((rc = grow(h, &h->d_gray, &h->cap_gray, (size_t)chunk * img_sz))) return rc; }
+        for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+            const int64_t m = std::min(chunk, n - i0);
+            uint8_t* gd = g ? g + i0 * img_sz : h->d_gray;
+            if ((rc = launch_preprocess(h, h->stream, frames + i0 * frame_sz, m, fh, fw, gd))) return rc;
+            if (detect && (rc = tail(h->stream, gd, m, probs ? probs + i0 * nc : nullptr, cls ? cls + i0 : nullptr, bbox ? bbox + i0 * 4 : nullptr))) return rc;
+        }
+        return CNNACC_OK;
+    }
+
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)16 << 20) / frame_sz)));
+    if (detect && (rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)hchunk * img_sz))) return rc;
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
+        const int64_t m = std::min(hchunk, n - i0);
+        Slot& s = h->slots[ci % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * frame_sz, hchunk * img_sz, hchunk))) return rc;
+        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, frames + i0 * frame_sz, m * frame_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        if ((rc = launch_preprocess(h, h->st_k, s.d_in, m, fh, fw, s.d_out))) return rc;
+        if (detect && (rc = tail(h->st_k, s.d_out, m, s.d_probs, s.d_cls, s.d_bbox))) return rc;
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        if (gray128) CU(h, cudaMemcpyAsync(gray128 + i0 * img_sz, s.d_out, m * img_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+        if (detect) {
+            if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
+            if (cls)   CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+            if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+        }
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+    }
+    CU(h, cudaStreamSynchronize(h->st_d2h));
+    return detect ? check_fused_status(h) : CNNACC_OK;
+}
+
+int cnnacc_preprocess_bgr(cnnacc_handle* h, const uint8_t* frames, int64_t n, int fh, int fw, uint8_t* gray128, uint32_t flags) {
+    return frames_impl(h, frames, n, fh, fw, gray128, nullptr, nullptr, nullptr, false, flags);
+}
+
+int cnnacc_detect_frames(cnnacc_handle* h, const uint8_t* frames, int64_t n, int fh, int fw, uint8_t* gray128,
+                         float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
+    return frames_impl(h, frames, n, fh, fw, gray128, probs, cls, bbox, true, flags);
 }
 
 int cnnacc_alloc_host(size_t bytes, void** out) {

@@ -133,6 +133,19 @@ int cnnacc_infer_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n,
 int cnnacc_cam_bbox_batch(cnnacc_handle *h, const uint8_t *feats, int64_t n, const int32_t *cls,
                           int32_t *bbox, uint8_t *cam, uint32_t flags);
 
+/* ---- the step in front of the hot path in the real-time loop (realtime_detect.py:582-591) ------------------
+ * preprocess_bgr: frames [n][fh][fw][3] u8 BGR (cv2 frames) -> gray128 [n][128][128] u8 =
+ *                 centre-crop to the square of side min(fh,fw), cv2.cvtColor(BGR2GRAY), cv2.resize((128,128), INTER_AREA);
+ *                 OpenCV's fixed-point gray and all three INTER_AREA arithmetic paths are reproduced bit for bit
+ *                 (pinned against cv2 4.13.0).  The crop side must be 128..8192.
+ * detect_frames : one iteration of the loop body (:582-598) per frame: preprocess -> conv stack -> classify_vec -> bbox_vec
+ *                 (or get_cam_bbox with CNNACC_FLAG_BBOX_UPSAMPLED) without anything but the predictions leaving the GPU;
+ *                 gray128 may be NULL; probs / cls / bbox as in classify_batch. */
+int cnnacc_preprocess_bgr(cnnacc_handle *h, const uint8_t *frames, int64_t n, int fh, int fw,
+                          uint8_t *gray128, uint32_t flags);
+int cnnacc_detect_frames(cnnacc_handle *h, const uint8_t *frames, int64_t n, int fh, int fw, uint8_t *gray128,
+                         float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
+
 /* ---- host memory the DMA engines can stream from (pynq.allocate, realtime_detect.py:293,301) */
 int cnnacc_alloc_host(size_t bytes, void **out);
 int cnnacc_free_host(void *p);

@@ -36,3 +36,8 @@ def tail_golden():
 @pytest.fixture(scope="session")
 def cam_golden():
     return np.load(os.path.join(GOLDEN, "cam_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def prep_golden():
+    return np.load(os.path.join(GOLDEN, "prep_cases.npz"))

@@ -149,3 +149,33 @@ CAM_CASES = [
     dict(name="cam_zeros", features="zeros", n=1),
     dict(name="cam_full", features="full", n=1),
 ]
+
+
+def make_frames(kind, n, h, w):
+    """Synthetic (n,h,w,3) u8 BGR camera frames.  kind: ('rng', seed) | ('smooth', seed) | ('edges', seed)."""
+    tag, seed = kind
+    rng = np.random.default_rng(seed)
+    if tag == "rng":
+        return rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    if tag == "smooth":
+        hh, ww = -(-h // 16) * 16, -(-w // 16) * 16
+        return np.stack([smooth_images(seed * 3 + c, n, hh, ww)[:, :h, :w] for c in range(3)], axis=-1)
+    if tag == "edges":                              # saturated blocks: exercises rounding ties and 0 / 255 extremes
+        blocks = rng.integers(0, 2, (n, -(-h // 7), -(-w // 5), 3), dtype=np.uint8) * 255
+        return np.repeat(np.repeat(blocks, 7, axis=1), 5, axis=2)[:, :h, :w].copy()
+    raise ValueError(kind)
+
+
+# pre-processing cases pinned by tests/golden/prep_cases.npz (tests/golden/make_prep_golden.py; cv2 4.13.0)
+PREP_CASES = [
+    dict(name="vga_rng", frames=("rng", 50), n=2, h=480, w=640),            # the reference's camera size (realtime_detect.py:151)
+    dict(name="vga_smooth", frames=("smooth", 51), n=2, h=480, w=640),
+    dict(name="vga_edges", frames=("edges", 52), n=2, h=480, w=640),
+    dict(name="portrait_720", frames=("rng", 53), n=1, h=1280, w=720),      # h > w branch, fractional scale 5.625
+    dict(name="square_300", frames=("smooth", 54), n=1, h=300, w=300),      # no crop, scale 2.34
+    dict(name="x2_256", frames=("edges", 55), n=2, h=256, w=320),           # integer scale 2: (sum + 2) >> 2
+    dict(name="x3_384", frames=("edges", 56), n=2, h=384, w=384),           # integer scale 3: rint(sum * (1/9))
+    dict(name="x6_768", frames=("rng", 57), n=1, h=768, w=1024),            # integer scale 6
+    dict(name="x1_128", frames=("rng", 58), n=1, h=128, w=160),             # scale 1: gray only
+    dict(name="odd_131", frames=("rng", 59), n=1, h=131, w=200),            # scale just above 1
+]

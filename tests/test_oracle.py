@@ -185,3 +185,24 @@ def test_cam_threshold_is_an_integer_level_rule():
     for v in cams:
         rng.shuffle(v)
         assert float_rule(v.reshape(128, 128)) == np_oracle.get_cam_bbox_levels(v.reshape(128, 128))
+
+
+# ---- pre-processing (realtime_detect.py:582-591): OpenCV's BGR2GRAY + INTER_AREA restated ------------------------
+
+@pytest.mark.parametrize("case", inputs.PREP_CASES, ids=lambda c: c["name"])
+def test_preprocess_oracle_matches_cv2_fixtures(case, prep_golden):
+    frames = inputs.make_frames(case["frames"], case["n"], case["h"], case["w"])
+    got = np.stack([np_oracle.preprocess_bgr(f) for f in frames])
+    assert np.array_equal(got, prep_golden[case["name"]])
+
+
+def test_area_table_properties():
+    for S in (129, 200, 300, 480, 720, 1000):
+        tab = np_oracle.area_tab(S, 128)
+        w = np.zeros(128)
+        for d, s, a in tab:
+            assert 0 <= s < S and a > 0
+            w[d] += a
+        assert np.allclose(w, 1.0, atol=1e-6)                     # each output pixel's weights sum to 1
+        src = [s for _, s, _ in tab]
+        assert src[0] == 0 and src[-1] == S - 1 and all(b - a in (0, 1) for a, b in zip(src, src[1:]))
