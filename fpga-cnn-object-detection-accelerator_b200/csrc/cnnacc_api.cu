@@ -25,6 +25,8 @@ using namespace cnnacc;
 namespace {
 
 constexpr int kSlots = 4;                       // staging buffers in flight for host-pointer batches
+constexpr int kSmallN = 64;                     // calls up to this many units skip the staging ring (latency path)
+constexpr size_t kSmallPredBytes = (size_t)kSmallN * (16 + kMaxClasses * 4 + 4);   // bbox | probs | cls
 constexpr size_t kBramBytes = 16 * 4096 + 32 * 1024 + 64 * 256;   // 112-channel feature-BRAM mirror
 
 struct Slot {
@@ -59,6 +61,8 @@ struct cnnacc_handle {
     int prep_side = 0; AreaTabHost prep_tab;
     int *d_prep_start = nullptr, *d_prep_cnt = nullptr; float* d_prep_alpha = nullptr; size_t cap_prep_alpha = 0;
     uint8_t* d_gray = nullptr; size_t cap_gray = 0;
+    // small calls (<= kSmallN units): everything on one stream, predictions come back in one copy through pinned memory
+    uint8_t *d_pred_small = nullptr, *h_pred_small = nullptr;
     // single-image protocol state
     uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned + mapped: the batch-1 path runs zero-copy on them
     uint8_t *h_img_dev = nullptr, *h_bram_dev = nullptr;   // their device addresses
@@ -301,6 +305,8 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer(&h->h_img_dev, h->h_img, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostGetDevicePointer(&h->h_bram_dev, h->h_bram, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if ((e = cudaHostAlloc(&h->h_pred_small, kSmallPredBytes, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaMalloc(&h->d_pred_small, kSmallPredBytes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_img1, CNNACC_IMG * CNNACC_IMG)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_bram, kBramBytes)) != cudaSuccess) return bail("cudaMalloc", e);
     *out = h;
@@ -320,7 +326,7 @@ int cnnacc_destroy(cnnacc_handle* h) {
     cudaFree(h->d_wdirect); cudaFree(h->d_fcw); cudaFree(h->d_fcb);
     cudaFree(h->d_l0); cudaFree(h->d_l1); cudaFree(h->d_feat); cudaFree(h->d_img1); cudaFree(h->d_bram);
     fused_free(h->fused);
-    cudaFreeHost(h->h_img); cudaFreeHost(h->h_bram);
+    cudaFreeHost(h->h_img); cudaFreeHost(h->h_bram); cudaFreeHost(h->h_pred_small); cudaFree(h->d_pred_small);
     cudaEvent_t evs[] = {h->ev_t0, h->ev_t1, h->ev_a, h->ev_b, h->ev_c, h->ev_done};
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -570,6 +576,25 @@ int cnnacc_load_classifier(cnnacc_handle* h, const float* fc_w, const float* fc_
     return CNNACC_OK;
 }
 
+// Predictions of a small call: one contiguous device block [bbox m x 4 i32 | probs m x nc f32 | cls m i32], one D2H into
+// pinned memory, then plain copies into the caller's arrays.
+struct SmallPred {
+    float* d_probs; int32_t* d_cls; int32_t* d_bbox; size_t bytes; size_t off_probs, off_cls;
+};
+static SmallPred small_pred(cnnacc_handle* h, int64_t m) {
+    SmallPred p;
+    p.off_probs = (size_t)m * 16; p.off_cls = p.off_probs + (size_t)m * h->n_cls * 4; p.bytes = p.off_cls + (size_t)m * 4;
+    p.d_bbox = reinterpret_cast<int32_t*>(h->d_pred_small);
+    p.d_probs = reinterpret_cast<float*>(h->d_pred_small + p.off_probs);
+    p.d_cls = reinterpret_cast<int32_t*>(h->d_pred_small + p.off_cls);
+    return p;
+}
+static void small_pred_unpack(cnnacc_handle* h, const SmallPred& p, int64_t m, float* probs, int32_t* cls, int32_t* bbox, bool cls_given) {
+    if (bbox) std::memcpy(bbox, h->h_pred_small, (size_t)m * 16);
+    if (probs) std::memcpy(probs, h->h_pred_small + p.off_probs, (size_t)m * h->n_cls * 4);
+    if (cls && !cls_given) std::memcpy(cls, h->h_pred_small + p.off_cls, (size_t)m * 4);
+}
+
 // shared body of classify_batch / infer_batch
 static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool src_is_images,
                         float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
@@ -612,6 +637,26 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    if (n <= kSmallN) {                                      // latency path: one stream, one result copy
+        Slot& s = h->slots[0];
+        cudaStream_t st = h->st_k;
+        if ((rc = slot_reserve(h, s, n * img_sz, src_is_images ? n * img_sz : 0, 0))) return rc;
+        if (maps && (rc = ensure_maps(h, n, CNNACC_IMG, CNNACC_IMG))) return rc;
+        const SmallPred p = small_pred(h, n);
+        CU(h, cudaMemcpyAsync(s.d_in, src, n * img_sz, cudaMemcpyHostToDevice, st));
+        if (cls_given) CU(h, cudaMemcpyAsync(p.d_cls, cls, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        const uint8_t* f = s.d_in;
+        if (src_is_images) {
+            if ((rc = conv_stack_device(h, st, s.d_in, n, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+            f = s.d_out;
+        }
+        if ((rc = launch_tail(h, st, f, n, p.d_probs, p.d_cls, upsampled ? nullptr : p.d_bbox, cls_given))) return rc;
+        if (bbox && upsampled && (rc = launch_cam_upsampled(h, st, f, n, p.d_cls, p.d_bbox, nullptr))) return rc;
+        CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        small_pred_unpack(h, p, n, probs, cls, bbox, cls_given);
+        return src_is_images ? check_fused_status(h) : CNNACC_OK;
+    }
     const int64_t hchunk = std::min<int64_t>(n, 4096);
     if (maps && (rc = ensure_maps(h, hchunk, CNNACC_IMG, CNNACC_IMG))) return rc;
     int64_t ci = 0;
@@ -728,6 +773,20 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    if (n <= kSmallN && n * frame_sz <= ((size_t)64 << 20)) {   // latency path: one stream, one result copy
+        Slot& s = h->slots[0];
+        cudaStream_t st = h->st_k;
+        if ((rc = slot_reserve(h, s, n * frame_sz, n * img_sz, 0))) return rc;
+        const SmallPred p = small_pred(h, n);
+        CU(h, cudaMemcpyAsync(s.d_in, frames, n * frame_sz, cudaMemcpyHostToDevice, st));
+        if ((rc = launch_preprocess(h, st, s.d_in, n, fh, fw, s.d_out))) return rc;
+        if (detect && (rc = tail(st, s.d_out, n, p.d_probs, p.d_cls, p.d_bbox))) return rc;
+        if (gray128) CU(h, cudaMemcpyAsync(gray128, s.d_out, n * img_sz, cudaMemcpyDeviceToHost, st));
+        if (detect) CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        if (detect) small_pred_unpack(h, p, n, probs, cls, bbox, false);
+        return detect ? check_fused_status(h) : CNNACC_OK;
+    }
     // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)16 << 20) / frame_sz)));
     if (detect && (rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)hchunk * img_sz))) return rc;

@@ -15,7 +15,7 @@
 //                          to fp32 on its own (no FMA), weights from computeResizeAreaTab in double -> float.
 // The weight table (same for x and y: the crop is square) is built on the host by make_area_tab below.
 //
-// Work split: one CTA of 128 threads per (4 output rows, frame); thread = output column.  A VGA frame is 900 KiB in and
+// Work split: one CTA of 128 threads per (output row, frame); thread = output column.  A VGA frame is 900 KiB in and
 // 16 KiB out, so the kernel is bound by HBM reads of the frames (and, end to end, by PCIe bringing them in).
 #pragma once
 #include <cmath>
@@ -24,7 +24,7 @@
 
 namespace cnnacc {
 
-constexpr int kPrepOut = 128, kPrepRowsPerCta = 4, kPrepMaxSide = 8192;
+constexpr int kPrepOut = 128, kPrepRowsPerCta = 1, kPrepMaxSide = 8192;
 
 enum PrepMode : int { kPrepCopy = 0, kPrepBox2 = 1, kPrepBoxK = 2, kPrepFrac = 3 };
 
