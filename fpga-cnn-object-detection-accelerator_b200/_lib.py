@@ -36,6 +36,7 @@ SYMBOLS = {
     "cnnacc_load_classifier": (_c.c_int, [_H, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "cnnacc_classify_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32]),
     "cnnacc_infer_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32]),
+    "cnnacc_pool_features": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_uint32]),
     "cnnacc_cam_bbox_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32]),
     "cnnacc_preprocess_bgr": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
     "cnnacc_detect_frames": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,

@@ -232,6 +232,16 @@ class CNNAccelerator:
         bbox='vec': realtime_detect.bbox_vec; bbox='upsampled': pynq_inference.Classifier.get_cam_bbox."""
         return self._predict(self._libc.cnnacc_classify_batch, features, bbox=bbox)
 
+    def pool_features(self, features):
+        """features [N,64,256] u8 -> [N,1024] f32 spatial-bin pooled, /255 (retrain_classifier.py:188-205): the trainer's input."""
+        x = np.ascontiguousarray(features, dtype=np.uint8)
+        n = x.shape[0]
+        if x.ndim < 2 or x[0].size != 16384:
+            raise ValueError("expected [N,64,256] features")
+        out = np.empty((n, 1024), dtype=np.float32)
+        self._check(self._libc.cnnacc_pool_features(self._h, _vp(x), n, _vp(out), 0))
+        return out
+
     def cam_bbox_batch(self, features, cls, return_cam=False):
         """Classifier.get_cam_bbox (pynq_inference.py:349-408) for given classes: features [N,64,256] u8 + cls [N] i32
         -> bbox [N,4] i32 (x1,y1,x2,y2), and with return_cam the upsampled maps [N,128,128] u8 (cam_full = maps/255)."""
@@ -392,6 +402,14 @@ class Classifier:
         bbox, cam = self._acc.cam_bbox_batch(np.asarray(features, dtype=np.uint8).reshape(1, 64, 256),
                                              np.array([class_idx], dtype=np.int32), return_cam=True)
         return cam[0].astype(np.float32) / 255.0, tuple(int(v) for v in bbox[0])
+
+
+def load_features(path):
+    """Read a feature dump written by dump_features or by the reference's dumpers (retrain_classifier.py:155-158):
+    -> (features (N,64,256) u8, labels (N,), names, shifts or None)."""
+    data = np.load(path, allow_pickle=False)
+    return (data["features"], data["labels"], list(data["names"]) if "names" in data else None,
+            tuple(int(v) for v in data["shifts"]) if "shifts" in data else None)
 
 
 def dump_features(acc, images, labels, names, output, shifts=None):

@@ -695,6 +695,44 @@ int cnnacc_infer_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, float* 
     return predict_impl(h, imgs, n, true, probs, cls, bbox, flags);
 }
 
+int cnnacc_pool_features(cnnacc_handle* h, const uint8_t* feats, int64_t n, float* pooled, uint32_t flags) {
+    int rc;
+    if (!h) return CNNACC_ERR_ARG;
+    if (n < 0) return fail(h, CNNACC_ERR_ARG, "negative n");
+    if (n == 0) return CNNACC_OK;
+    if (!feats || !pooled) return fail(h, CNNACC_ERR_ARG, "NULL feature / output pointer");
+    CU(h, cudaSetDevice(h->device));
+    const size_t feat_sz = CNNACC_FEAT_BYTES, out_sz = 1024 * sizeof(float);
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        pool_features_kernel<<<(unsigned)n, 256, 0, h->stream>>>(feats, pooled);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return CNNACC_OK;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    const int64_t hchunk = std::min<int64_t>(n, 2048);
+    int64_t ci = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
+        const int64_t m = std::min(hchunk, n - i0);
+        Slot& s = h->slots[ci % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * feat_sz, hchunk * out_sz, 0))) return rc;
+        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, feats + i0 * feat_sz, m * feat_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        pool_features_kernel<<<(unsigned)m, 256, 0, h->st_k>>>(s.d_in, reinterpret_cast<float*>(s.d_out));
+        h->launches++;
+        CU(h, cudaGetLastError());
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        CU(h, cudaMemcpyAsync(pooled + i0 * 1024, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+    }
+    CU(h, cudaStreamSynchronize(h->st_d2h));
+    return CNNACC_OK;
+}
+
 int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, const int32_t* cls, int32_t* bbox, uint8_t* cam,
                           uint32_t flags) {
     int rc;

@@ -176,4 +176,28 @@ classify_bbox_kernel(const uint8_t* __restrict__ feats, const float* __restrict_
     }
 }
 
+// Spatial-bin pooled features alone: (64,256) u8 -> (1024,) f32, pooled[ch*16 + r*4 + c] = mean(4x4 bin) / 255 -- the
+// classifier's input, which the reference's trainer builds from a feature dump (retrain_classifier.py:188-205) and
+// Classifier.classify builds per image (pynq_inference.py:325-334).  Bin sums are exact integers and sum/16 is exact,
+// so one correctly rounded division S/4080 equals the reference's mean-then-/255.
+__global__ void __launch_bounds__(256)
+pool_features_kernel(const uint8_t* __restrict__ feats, float* __restrict__ pooled)
+{
+    const int t = threadIdx.x;
+    const size_t img = blockIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(feats + img * 16384);
+    int S[4] = {0, 0, 0, 0};                     // thread t: channel t/4, bin-row t%4 -> bins 4t .. 4t+3
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint4 v = __ldg(src + t * 4 + r);
+        S[0] = __dp4a(v.x, 0x01010101u, (unsigned)S[0]);
+        S[1] = __dp4a(v.y, 0x01010101u, (unsigned)S[1]);
+        S[2] = __dp4a(v.z, 0x01010101u, (unsigned)S[2]);
+        S[3] = __dp4a(v.w, 0x01010101u, (unsigned)S[3]);
+    }
+    reinterpret_cast<float4*>(pooled + img * 1024)[t] =
+        make_float4(__fdiv_rn((float)S[0], 4080.0f), __fdiv_rn((float)S[1], 4080.0f),
+                    __fdiv_rn((float)S[2], 4080.0f), __fdiv_rn((float)S[3], 4080.0f));
+}
+
 }  // namespace cnnacc

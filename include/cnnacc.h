@@ -126,6 +126,10 @@ int cnnacc_classify_batch(cnnacc_handle *h, const uint8_t *feats, int64_t n,
                           float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
 int cnnacc_infer_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n,
                        float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
+/* pool_features  : feats [n][64][256] u8 -> pooled [n][1024] f32, pooled[ch*16 + r*4 + c] = mean(4x4 bin) / 255: the classifier
+ *                  input the trainer builds from a feature dump (retrain_classifier.py:188-205; pynq_inference.py:325-334).
+ *                  Exact: equal to the numpy result bit for bit.  Needs no weights or classifier. */
+int cnnacc_pool_features(cnnacc_handle *h, const uint8_t *feats, int64_t n, float *pooled, uint32_t flags);
 /* cam_bbox_batch : Classifier.get_cam_bbox(features, class_idx, img_size=128) (pynq_inference.py:349-408) per image:
  *                  feats [n][64][256] u8, cls [n] i32 (the class_idx argument) -> bbox [n][4] i32 (x1,y1,x2,y2) and,
  *                  when cam != NULL, cam [n][128][128] u8 = the upsampled map (the reference's cam_full is cam/255 as f32).

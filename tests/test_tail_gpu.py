@@ -186,3 +186,27 @@ def test_cam_bbox_object_surface_and_pipeline(conv_golden, cam_golden, shipped_w
     with pytest.raises(ValueError):
         a.classify_batch(f, bbox="nope")
     a.close()
+
+
+def test_pool_features_and_dump_round_trip(tmp_path, acc, shipped_weights):
+    """The data format either side of the path: feature dump (.npz) and the trainer's pooled input (retrain_classifier.py:155-205)."""
+    import fpga_cnn_b200 as fc
+    feats = np.concatenate([inputs.make_features(("rng", 70), 40), inputs.make_features(("low", 71), 30),
+                            inputs.make_features("full", 1), inputs.make_features("zeros", 1)])
+    pooled = acc.pool_features(feats)
+    assert pooled.dtype == np.float32 and pooled.shape == (72, 1024)
+    assert np.array_equal(pooled, np_oracle.pool_bins(feats))                   # exact, not approximately equal
+    big = inputs.make_features(("rng", 72), 2500)                                 # more than one staging chunk
+    assert np.array_equal(acc.pool_features(big), np_oracle.pool_bins(big))
+    # Classifier.classify's pooled vector is the same thing (pynq_inference.py:325-334)
+    for i in (0, 41):
+        assert np.array_equal(pooled[i], np_oracle.classify_vec(feats[i], *inputs.make_fc())[3]) or \
+               np.abs(pooled[i] - np_oracle.classify_vec(feats[i], *inputs.make_fc())[3]).max() <= 6e-8
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    imgs = inputs.make_images(("rng", 5), 6)
+    out = tmp_path / "feats.npz"
+    f = fc.dump_features(a, imgs, labels=[0, 1, 2, 3, 4, -1], names=[f"im{i}" for i in range(6)], output=str(out), shifts=(7, 10, 11))
+    f2, labels, names, shifts = fc.load_features(str(out))
+    assert np.array_equal(f, f2) and list(labels) == [0, 1, 2, 3, 4, -1] and names[5] == "im5" and shifts == (7, 10, 11)
+    a.close()
