@@ -211,3 +211,51 @@ def test_device_pointer_path_with_torch(fc, shipped_weights, conv_golden):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().reshape(8, 64, 256), conv_golden["rng_shipped_mid"])
     a.close()
+
+
+def test_handle_lifecycle_and_mixed_call_sizes(fc, port, shipped_weights):
+    """Handles are created and destroyed repeatedly, two live side by side, and one handle sees call sizes that grow, shrink
+    and switch between the latency path, the staging ring and device pointers -- every result still byte-equal to the oracle."""
+    import torch
+    imgs = inputs.make_images(("rng", 31), 700)
+    want = oracle.port_infer_batch(port, imgs, shipped_weights, (7, 10, 11)).reshape(700, 64, 16, 16)
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(6):
+        a, b = fc.CNNAccelerator(), fc.CNNAccelerator()
+        for h in (a, b):
+            h.load_weights(shipped_weights)
+            h.set_shifts(7, 10, 11)
+        for n in (1, 700, 3, 65, 64, 300, 2):
+            got = (a if n % 2 else b).run_batch(imgs[:n])
+            assert np.array_equal(got, want[:n]), n
+        t = torch.from_numpy(imgs[:130]).cuda()
+        assert np.array_equal(a.run_batch(t).cpu().numpy(), want[:130])
+        a.close()
+        b.close()
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < (64 << 20)          # nothing substantial leaked across 12 handles
+
+
+def test_two_host_threads_two_handles(fc, port, shipped_weights):
+    """One handle per host thread: concurrent run_batch calls do not disturb each other."""
+    import threading
+    imgs = [inputs.make_images(("rng", 40 + i), 400) for i in range(2)]
+    want = [oracle.port_infer_batch(port, im, shipped_weights, (2, 4, 6)).reshape(400, 64, 16, 16) for im in imgs]
+    accs = [fc.CNNAccelerator() for _ in range(2)]
+    for a in accs:
+        a.load_weights(shipped_weights)
+    bad = []
+
+    def work(i):
+        for _ in range(10):
+            if not np.array_equal(accs[i].run_batch(imgs[i]), want[i]):
+                bad.append(i)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for a in accs:
+        a.close()
+    assert not bad
