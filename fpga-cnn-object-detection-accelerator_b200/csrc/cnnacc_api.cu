@@ -429,9 +429,25 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
     size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
     if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
-    int64_t ci = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
-        const int64_t m = std::min(hchunk, n - i0);
+    // Chunk sizes ramp up at the start and down at the end (1/4, 1/2, 1, ..., 1, 1/2, 1/4 of hchunk for depth 2): the first
+    // H2D and the last D2H run alone on the link, so the shorter they are the sooner both directions are busy together.
+    static const int ramp = [] { const char* e = getenv("CNNACC_HOST_RAMP"); int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
+    const int depth = (n >= 4 * hchunk && (hchunk >> ramp) >= 1) ? ramp : 0;
+    const int64_t tail_total = hchunk - (hchunk >> depth);                           // h/2 + h/4 + ... + h/2^depth
+    int64_t ci = 0, m = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += m, ci++) {
+        m = hchunk;
+        if (depth) {
+            const int64_t left = n - i0;
+            if (ci < depth) m = hchunk >> (depth - ci);                              // ramp up
+            else if (left <= tail_total) {                                           // ramp down: largest h/2^j that fits, remainder first
+                int64_t piece = hchunk >> 1, rest = tail_total;
+                while (piece > 1 && left <= rest - piece) { rest -= piece; piece >>= 1; }
+                m = left - (rest - piece);
+            } else if (left < hchunk + tail_total) m = left - tail_total;            // the last full-size piece takes the remainder
+            m = std::max<int64_t>(m, 1);
+        }
+        m = std::min(m, n - i0);
         Slot& s = h->slots[ci % kSlots];
         if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
         if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));       // slot drained (its kernels ended earlier)
