@@ -130,16 +130,22 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
         return 0;
     }
     if (tiled_ok(h, H, W, flags)) {
-        // larger images: overlapping 128x128 windows through the fused kernel (tiling.cuh); d_l0 / d_l1 hold the windows
-        // and their 16x16 feature tiles
+        // larger images: overlapping 128x128 windows through the fused kernel (tiling.cuh)
         const TilePlan py = make_tile_plan(H / 8), px = make_tile_plan(W / 8);
         const int64_t n_t = n * py.n * px.n;
         if (n_t > 0x7fffffff) return fail(h, CNNACC_ERR_ARG, "too many tiles in one chunk");
-        gather_tiles_kernel<<<(unsigned)n_t, 256, 0, stream>>>(d_imgs, d_l0, H, W, py, px);
-        int rc = launch_fused(h->fused, stream, d_l0, n_t, d_l1, h->shifts, h->sm_count, nullptr, nullptr);
-        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch (tiled): ") + cudaGetErrorString((cudaError_t)rc));
+        // the fused kernel reads each window straight out of the big image (TMA box at the window origin, zero fill beyond
+        // the image border); its 16x16 feature tiles land in d_l1 and the scatter kernel keeps what each window owns
+        CUtensorMap map;
+        int rc = fused_encode_map(d_imgs, n, &map, H, W);
+        if (rc == 0) {
+            FusedWindows win;
+            win.ntx = px.n; win.nty = py.n; win.gx = px.g; win.gy = py.g;
+            rc = launch_fused_map(h->fused, stream, map, n_t, d_l1, h->shifts, h->sm_count, nullptr, nullptr, &win);
+        }
+        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch (windows): ") + cudaGetErrorString((cudaError_t)rc));
         scatter_features_kernel<<<(unsigned)n_t, 256, 0, stream>>>(d_l1, d_feats, H / 8, W / 8, py, px);
-        h->launches += 3;
+        h->launches += 2;
         CU(h, cudaGetLastError());
         return 0;
     }
@@ -163,9 +169,9 @@ int64_t chunk_images(int H, int W) {
 
 int ensure_maps(cnnacc_handle* h, int64_t n, int H, int W) {
     int rc;
-    // per-layer path: the two intermediate maps; tiled path: the 128x128 windows and their feature tiles
+    // per-layer path: the two intermediate maps; window path: the 16x16 feature tiles of the windows (in d_l1)
     const size_t tiles = (H >= CNNACC_IMG && W >= CNNACC_IMG) ? (size_t)n * tiles_per_dim(H / 8) * tiles_per_dim(W / 8) * 16384 : 0;
-    if ((rc = grow(h, &h->d_l0, &h->cap_l0, std::max((size_t)n * 16 * (H / 2) * (W / 2), tiles)))) return rc;
+    if ((rc = grow(h, &h->d_l0, &h->cap_l0, (size_t)n * 16 * (H / 2) * (W / 2)))) return rc;
     if ((rc = grow(h, &h->d_l1, &h->cap_l1, std::max((size_t)n * 32 * (H / 4) * (W / 4), tiles)))) return rc;
     return 0;
 }

@@ -140,6 +140,11 @@ struct FusedParams {
     uint8_t* dump_l1;            // optional [n][32][32][32]
     int* status;                 // device int, OR-ed error bits
     int* status_host;            // the same in mapped pinned host memory: polled without a CUDA call
+    // window mode (images larger than 128x128, tiling.cuh): unit u = window (u % win_ntx, (u / win_ntx) % win_nty) of image
+    // u / (win_ntx * win_nty); the TMA box is read straight from the big image at pixel origin 8 * win_g{x,y}[..] (origins are
+    // even, so x stays 16-byte aligned).  win_ntx == 0: unit u = image u of an [n][128][128] array.
+    int win_ntx, win_nty;
+    short win_gx[80], win_gy[80];
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -205,9 +210,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 3D tiled TMA load (x, y, image) -> smem, completion on an mbarrier.
-__device__ __forceinline__ void tma_load_image(uint32_t dst, const CUtensorMap* map, uint32_t bar, int img) {
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int img) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 :: "r"(dst), "l"(map), "r"(-16), "r"(-1), "r"(img), "r"(bar) : "memory");
+                 :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(img), "r"(bar) : "memory");
 }
 // 1D bulk copy global -> smem (pre-packed weights).
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -290,6 +295,19 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         if (mbar_try(b, parity)) return;                 // fast path: already complete
         // ~0.1 s budget; once any wait has timed out every later wait gives up quickly so the CTA drains
         if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : 200000000LL)) atomicOr(s_err, code);
+    };
+
+    // TMA load of unit u (an image, or a window of a larger image) into an input slot; the box starts one pixel row above
+    // and 16 bytes left of the unit's first pixel, out-of-bounds bytes arrive as zeros = the conv padding at image borders.
+    auto tma_load_unit = [&](uint32_t dst, uint32_t b, int u) {
+        int x = -16, y = -1, img = u;
+        if (P.win_ntx) {
+            const int per = P.win_ntx * P.win_nty, w = u % per;
+            img = u / per;
+            x += 8 * P.win_gx[w % P.win_ntx];
+            y += 8 * P.win_gy[w / P.win_ntx];
+        }
+        tma_load_box(dst, &in_map, b, x, y, img);
     };
 
     if (warp < kL0Warps) {
@@ -543,7 +561,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             bulk_load(s_base + kOffB2, P.b2, kB2Bytes, bar(kBarW));
             for (int k = 0; k < 2 && k < n_local; k++) {
                 mbar_expect_tx(bar(kBarInFull0 + k), kInBytes);
-                tma_load_image(s_base + (k ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + k), (int)blockIdx.x + k * (int)gridDim.x);
+                tma_load_unit(s_base + (k ? kOffIn1 : kOffIn0), bar(kBarInFull0 + k), (int)blockIdx.x + k * (int)gridDim.x);
             }
         }
         __syncwarp();
@@ -565,8 +583,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                         wait_or_flag(bar(kBarInFree0 + slot), (uint32_t)(k >> 1) & 1, kErrSlotTimeout);
                         if (elect_one()) {
                             mbar_expect_tx(bar(kBarInFull0 + slot), kInBytes);
-                            tma_load_image(s_base + (slot ? kOffIn1 : kOffIn0), &in_map, bar(kBarInFull0 + slot),
-                                           (int)blockIdx.x + (k + 2) * (int)gridDim.x);
+                            tma_load_unit(s_base + (slot ? kOffIn1 : kOffIn0), bar(kBarInFull0 + slot),
+                                          (int)blockIdx.x + (k + 2) * (int)gridDim.x);
                         }
                         __syncwarp();
                     }
@@ -745,11 +763,12 @@ inline void fused_free(FusedWeights& fw) {
     fw.d_b1 = fw.d_b2 = nullptr; fw.d_status = nullptr; fw.h_status = fw.h_status_dev = nullptr; fw.ready = false;
 }
 
-// Tensor map over n images [n][128][128] u8 at a device-accessible address (device memory or mapped pinned host memory).
-inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map) {
-    if (n <= 0 || n > 0x7fffffff || (reinterpret_cast<uintptr_t>(d_imgs) & 15) || !get_encode_tiled()) return (int)cudaErrorInvalidValue;
-    const cuuint64_t gdim[3] = {128, 128, (cuuint64_t)n};
-    const cuuint64_t gstride[2] = {128, 16384};
+// Tensor map over n images [n][H][W] u8 (W a multiple of 16) at a device-accessible address (device memory or mapped
+// pinned host memory); the box is always the kernel's 160 x 130 input slot.
+inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map, int H = 128, int W = 128) {
+    if (n <= 0 || n > 0x7fffffff || (reinterpret_cast<uintptr_t>(d_imgs) & 15) || (W & 15) || !get_encode_tiled()) return (int)cudaErrorInvalidValue;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
     const cuuint32_t box[3] = {(cuuint32_t)kInPitch, (cuuint32_t)kInRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = get_encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(d_imgs), gdim, gstride, box, estr,
@@ -759,9 +778,20 @@ inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map) 
 }
 
 // One launch for the n images described by `map`.  Returns a cudaError_t as int (0 = launched).
+struct FusedWindows {             // window mode: see FusedParams
+    int ntx = 0, nty = 0;
+    const short *gx = nullptr, *gy = nullptr;
+};
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
-                            const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
+                            const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr) {
     FusedParams P;
+    P.win_ntx = P.win_nty = 0;
+    if (win) {
+        if (win->ntx < 1 || win->nty < 1 || win->ntx > 80 || win->nty > 80) return (int)cudaErrorInvalidValue;
+        P.win_ntx = win->ntx; P.win_nty = win->nty;
+        std::memcpy(P.win_gx, win->gx, win->ntx * sizeof(short));
+        std::memcpy(P.win_gy, win->gy, win->nty * sizeof(short));
+    }
     std::memcpy(P.w0, fw.w0, sizeof(P.w0));
     std::memcpy(P.w0f, fw.w0f, sizeof(P.w0f));
     P.shift0 = shifts[0]; P.shift1 = shifts[1]; P.shift2 = shifts[2];

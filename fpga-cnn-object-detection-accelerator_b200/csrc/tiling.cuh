@@ -44,23 +44,8 @@ inline TilePlan make_tile_plan(int Ho) {
 }
 inline int tiles_per_dim(int Ho) { return make_tile_plan(Ho).n; }
 
-// tiles[(img*nty + ty)*ntx + tx][128][128] <- imgs[img][8*gy .. +128][8*gx .. +128]
-__global__ void __launch_bounds__(256)
-gather_tiles_kernel(const uint8_t* __restrict__ imgs, uint8_t* __restrict__ tiles, int H, int W,
-                    const __grid_constant__ TilePlan py, const __grid_constant__ TilePlan px)
-{
-    const int64_t tile = blockIdx.x;
-    const int ntx = px.n, nty = py.n;
-    const int tx = (int)(tile % ntx), ty = (int)((tile / ntx) % nty);
-    const int64_t img = tile / ((int64_t)ntx * nty);
-    const int oy = 8 * py.g[ty], ox = 8 * px.g[tx];
-    const uint8_t* src = imgs + (size_t)img * H * W + (size_t)oy * W + ox;
-    uint2* dst = reinterpret_cast<uint2*>(tiles + (size_t)tile * 16384);
-    for (int i = threadIdx.x; i < 128 * 16; i += 256) {      // 16 x 8 bytes per row (origins are multiples of 8 pixels)
-        const int r = i >> 4, c = i & 15;
-        dst[i] = *reinterpret_cast<const uint2*>(src + (size_t)r * W + c * 8);
-    }
-}
+// The windows are not materialised: the fused kernel's TMA box reads window (ty, tx) of image img at pixel origin
+// (8*gx - 16, 8*gy - 1) of the big image (conv_fused.cuh, window mode; origins are even, so x stays 16-byte aligned).
 
 // feats[img][64][Ho][Wo] <- the outputs each tile owns out of tfeat[tile][64][16][16]
 __global__ void __launch_bounds__(256)
