@@ -135,18 +135,16 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
         const int64_t n_t = n * py.n * px.n;
         if (n_t > 0x7fffffff) return fail(h, CNNACC_ERR_ARG, "too many tiles in one chunk");
         // the fused kernel reads each window straight out of the big image (TMA box at the window origin, zero fill beyond
-        // the image border); its 16x16 feature tiles land in d_l1 and the scatter kernel keeps what each window owns
+        // the image border) and its epilogue stores the outputs the window computes exactly straight into d_feats
         CUtensorMap map;
         int rc = fused_encode_map(d_imgs, n, &map, H, W);
         if (rc == 0) {
             FusedWindows win;
-            win.ntx = px.n; win.nty = py.n; win.gx = px.g; win.gy = py.g;
-            rc = launch_fused_map(h->fused, stream, map, n_t, d_l1, h->shifts, h->sm_count, nullptr, nullptr, &win);
+            win.ntx = px.n; win.nty = py.n; win.ho = H / 8; win.wo = W / 8; win.gx = px.g; win.gy = py.g;
+            rc = launch_fused_map(h->fused, stream, map, n_t, d_feats, h->shifts, h->sm_count, nullptr, nullptr, &win);
         }
         if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch (windows): ") + cudaGetErrorString((cudaError_t)rc));
-        scatter_features_kernel<<<(unsigned)n_t, 256, 0, stream>>>(d_l1, d_feats, H / 8, W / 8, py, px);
-        h->launches += 2;
-        CU(h, cudaGetLastError());
+        h->launches += 1;
         return 0;
     }
     int rc;
@@ -156,9 +154,9 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
     return 0;
 }
 
-bool needs_maps(const cnnacc_handle* h, int H, int W, uint32_t flags) {
+bool needs_maps(const cnnacc_handle* h, int H, int W, uint32_t flags) {   // only the per-layer path has intermediate maps in HBM
     const bool fused_ok = (H == CNNACC_IMG && W == CNNACC_IMG) && !(flags & CNNACC_FLAG_DIRECT) && h->fused.ready;
-    return !fused_ok || (flags & CNNACC_FLAG_KEEP_MAPS);
+    return !(fused_ok || tiled_ok(h, H, W, flags)) || (flags & CNNACC_FLAG_KEEP_MAPS);
 }
 
 // images per chunk so that the per-layer workspaces stay around 512 MiB
@@ -169,10 +167,9 @@ int64_t chunk_images(int H, int W) {
 
 int ensure_maps(cnnacc_handle* h, int64_t n, int H, int W) {
     int rc;
-    // per-layer path: the two intermediate maps; window path: the 16x16 feature tiles of the windows (in d_l1)
-    const size_t tiles = (H >= CNNACC_IMG && W >= CNNACC_IMG) ? (size_t)n * tiles_per_dim(H / 8) * tiles_per_dim(W / 8) * 16384 : 0;
+    // per-layer path: the two intermediate maps
     if ((rc = grow(h, &h->d_l0, &h->cap_l0, (size_t)n * 16 * (H / 2) * (W / 2)))) return rc;
-    if ((rc = grow(h, &h->d_l1, &h->cap_l1, std::max((size_t)n * 32 * (H / 4) * (W / 4), tiles)))) return rc;
+    if ((rc = grow(h, &h->d_l1, &h->cap_l1, (size_t)n * 32 * (H / 4) * (W / 4)))) return rc;
     return 0;
 }
 

@@ -143,7 +143,10 @@ struct FusedParams {
     // window mode (images larger than 128x128, tiling.cuh): unit u = window (u % win_ntx, (u / win_ntx) % win_nty) of image
     // u / (win_ntx * win_nty); the TMA box is read straight from the big image at pixel origin 8 * win_g{x,y}[..] (origins are
     // even, so x stays 16-byte aligned).  win_ntx == 0: unit u = image u of an [n][128][128] array.
-    int win_ntx, win_nty;
+    // In window mode the features go straight to out[img][64][win_ho][win_wo]: every window stores the outputs it computes
+    // exactly (local rows/columns 1..14, plus 0 / 15 where the window touches the image border); neighbouring windows write
+    // identical bytes where those regions overlap.
+    int win_ntx, win_nty, win_ho, win_wo;
     short win_gx[80], win_gy[80];
 };
 
@@ -246,6 +249,8 @@ __device__ __forceinline__ uint32_t act_u8(int v, int shift) {
 // ---- the kernel ---------------------------------------------------------------------------------------------
 // Register budget: each SM sub-partition has 16 384 registers and 21 warps put 6 on one of them, so 80 per thread
 // (6 x 80 x 32 = 15 360) is the most that launches; 96 would need <= 20 warps.
+// kWin = window mode (FusedParams::win_*): a separate instantiation, so the 128x128 path carries none of its code.
+template <bool kWin>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FusedParams P)
 {
@@ -301,7 +306,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     // and 16 bytes left of the unit's first pixel, out-of-bounds bytes arrive as zeros = the conv padding at image borders.
     auto tma_load_unit = [&](uint32_t dst, uint32_t b, int u) {
         int x = -16, y = -1, img = u;
-        if (P.win_ntx) {
+        if constexpr (kWin) {
             const int per = P.win_ntx * P.win_nty, w = u % per;
             img = u / per;
             x += 8 * P.win_gx[w % P.win_ntx];
@@ -503,7 +508,19 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
 
             // ---- layer 2: 2 blocks of 128 pooling windows x 4 parities; -> staging (CHW) -> one 16 KiB TMA store ----
-            if (k > 0) {                                 // the previous image's store must have finished reading staging
+            constexpr bool win = kWin;
+            uint8_t* wbase = nullptr;                    // window mode: this lane's pixel in channel 0 of the big feature map
+            size_t wcs = 0;                              // ... and the channel stride
+            bool wrow = false;
+            int wgx = 0, wlo = 0, whi = 0;
+            if (win) {
+                const int per = P.win_ntx * P.win_nty, w = img % per, gy = P.win_gy[w / P.win_ntx], i = L >> 3;
+                wgx = P.win_gx[w % P.win_ntx];
+                wlo = wgx == 0 ? 0 : 1; whi = wgx == P.win_wo - 16 ? 15 : 14;
+                wrow = i >= (gy == 0 ? 0 : 1) && i <= (gy == P.win_ho - 16 ? 15 : 14);
+                wcs = (size_t)P.win_ho * P.win_wo;
+                wbase = P.out + ((size_t)(img / per) * 64 * P.win_ho + gy + i) * P.win_wo + wgx;
+            } else if (k > 0) {                          // the previous image's store must have finished reading staging
                 if (e == 0 && lane == 0) bulk_store_wait_read();
                 epi_bar_sync();
             }
@@ -540,14 +557,24 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kBarTmEmpty0 + h));
                     }
-                    uint8_t* o = smem + kOffStage + (cg * 16) * 256 + i * 16 + j;
+                    if (win) {
+                        if (wrow && j >= wlo && j <= whi) {
+                            uint8_t* o = wbase + (size_t)(cg * 16) * wcs + j;
 #pragma unroll
-                    for (int c = 0; c < 16; c++) o[c * 256] = (uint8_t)act_u8(m[c], P.shift2);
+                            for (int c = 0; c < 16; c++) o[c * wcs] = (uint8_t)act_u8(m[c], P.shift2);
+                        }
+                    } else {
+                        uint8_t* o = smem + kOffStage + (cg * 16) * 256 + i * 16 + j;
+#pragma unroll
+                        for (int c = 0; c < 16; c++) o[c * 256] = (uint8_t)act_u8(m[c], P.shift2);
+                    }
                 }
             }
-            fence_async_smem();
-            epi_bar_sync();
-            if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+            if (!win) {
+                fence_async_smem();
+                epi_bar_sync();
+                if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+            }
         }
         if (e == 0 && lane == 0) bulk_store_wait_all();
         if (e == 0) TRACE_END(1);
@@ -749,7 +776,8 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
     if ((e = cudaMemcpy(fw.d_b1, b1.data(), kB1Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpy(fw.d_b2, b2.data(), kB2Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if (!fw.attr_set) {
-        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
         fw.attr_set = true;
     }
     if (!get_encode_tiled()) return (int)cudaErrorNotSupported;
@@ -779,16 +807,16 @@ inline int fused_encode_map(const uint8_t* d_imgs, int64_t n, CUtensorMap* map, 
 
 // One launch for the n images described by `map`.  Returns a cudaError_t as int (0 = launched).
 struct FusedWindows {             // window mode: see FusedParams
-    int ntx = 0, nty = 0;
+    int ntx = 0, nty = 0, ho = 0, wo = 0;     // windows per row / column, feature-map size of the big image
     const short *gx = nullptr, *gy = nullptr;
 };
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
                             const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr) {
     FusedParams P;
-    P.win_ntx = P.win_nty = 0;
+    P.win_ntx = P.win_nty = P.win_ho = P.win_wo = 0;
     if (win) {
         if (win->ntx < 1 || win->nty < 1 || win->ntx > 80 || win->nty > 80) return (int)cudaErrorInvalidValue;
-        P.win_ntx = win->ntx; P.win_nty = win->nty;
+        P.win_ntx = win->ntx; P.win_nty = win->nty; P.win_ho = win->ho; P.win_wo = win->wo;
         std::memcpy(P.win_gx, win->gx, win->ntx * sizeof(short));
         std::memcpy(P.win_gy, win->gy, win->nty * sizeof(short));
     }
@@ -800,7 +828,8 @@ inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const C
     P.out = d_feats; P.dump_l0 = dump_l0; P.dump_l1 = dump_l1;
     P.status = fw.d_status; P.status_host = fw.h_status_dev;
     const int grid = (int)std::min<int64_t>(n, sm_count);
-    conv_stack_fused_kernel<<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    if (win) conv_stack_fused_kernel<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    else     conv_stack_fused_kernel<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
     return (int)cudaGetLastError();
 }
 

@@ -47,23 +47,9 @@ inline int tiles_per_dim(int Ho) { return make_tile_plan(Ho).n; }
 // The windows are not materialised: the fused kernel's TMA box reads window (ty, tx) of image img at pixel origin
 // (8*gx - 16, 8*gy - 1) of the big image (conv_fused.cuh, window mode; origins are even, so x stays 16-byte aligned).
 
-// feats[img][64][Ho][Wo] <- the outputs each tile owns out of tfeat[tile][64][16][16]
-__global__ void __launch_bounds__(256)
-scatter_features_kernel(const uint8_t* __restrict__ tfeat, uint8_t* __restrict__ feats, int Ho, int Wo,
-                        const __grid_constant__ TilePlan py, const __grid_constant__ TilePlan px)
-{
-    const int64_t tile = blockIdx.x;
-    const int ntx = px.n, nty = py.n;
-    const int tx = (int)(tile % ntx), ty = (int)((tile / ntx) % nty);
-    const int64_t img = tile / ((int64_t)ntx * nty);
-    const int gy = py.g[ty], gx = px.g[tx];
-    const int y0 = py.s[ty], ny = py.e[ty] - y0, x0 = px.s[tx], nx = px.e[tx] - x0;
-    const uint8_t* src = tfeat + (size_t)tile * 16384;
-    uint8_t* dst = feats + (size_t)img * 64 * Ho * Wo;
-    for (int i = threadIdx.x; i < 64 * ny * nx; i += 256) {
-        const int x = i % nx, y = (i / nx) % ny, c = i / (nx * ny);
-        dst[((size_t)c * Ho + y0 + y) * Wo + x0 + x] = src[c * 256 + (y0 + y - gy) * 16 + (x0 + x - gx)];
-    }
-}
+// Nor are the 16x16 feature tiles: the kernel's layer-2 epilogue stores every output a window computes exactly (local
+// rows / columns 1..14, plus 0 and 15 at image borders) straight into the big feature map; where neighbouring windows
+// overlap they write identical bytes.  The plan's [s, e) ranges document which window 'owns' an output and are what the
+// CPU tests check the plan with (cnnacc_tile_plan_host).
 
 }  // namespace cnnacc
