@@ -9,7 +9,10 @@
 #include <string>
 
 #include "conv_direct.cuh"
-#ifdef CNNACC_EXPERIMENT_V8            // tools/experiments: all three layers on tcgen05, two issuer warps (not the product)
+#if defined(CNNACC_EXPERIMENT_V9)      // tools/experiments: all three layers on tcgen05 (not the product)
+#include "../../tools/experiments/conv_fused_v9.cuh"
+#define CNNACC_EXPERIMENT_V8 1
+#elif defined(CNNACC_EXPERIMENT_V8)
 #include "../../tools/experiments/conv_fused_v8.cuh"
 #else
 #include "conv_fused.cuh"
