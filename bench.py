@@ -278,6 +278,33 @@ def run_reference_arm(args, weights):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+_ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so the pinned host buffers of the e2e leg (and the
+    copy-issuing thread) sit on the socket the GPU's PCIe root hangs off.  One process per GPU, as a deployment would run
+    it.  Returns a short description for the JSON line; CNNACC_BENCH_AFFINITY=0 turns it off."""
+    if os.environ.get("CNNACC_BENCH_AFFINITY", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        global _ORIG_AFFINITY
+        _ORIG_AFFINITY = os.sched_getaffinity(0)
+        cpus &= _ORIG_AFFINITY
+        if not cpus:
+            return "none reported"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cpus local to gpu {gpu_index} ({min(cpus)}-{max(cpus)})"
+    except Exception as e:                           # NVML missing or restricted: run unbound
+        return f"unavailable ({type(e).__name__})"
+
+
 def run_ours(args, weights):
     import torch
     import torch.distributed as dist
@@ -289,6 +316,7 @@ def run_ours(args, weights):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (ours): no CUDA device; there is no CPU fallback. Use --impl reference for the CPU arm.")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(local)          # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ddist = dist if world > 1 else None
@@ -462,6 +490,8 @@ def run_ours(args, weights):
     }
 
     if rank == 0:
+        if _ORIG_AFFINITY is not None:
+            os.sched_setaffinity(0, _ORIG_AFFINITY)  # the CPU baseline uses every core the process was given
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -484,7 +514,7 @@ def run_ours(args, weights):
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": Be * 16384, "d2h_bytes_per_step": Be * 16384,
-                    "batch": Be, "steps": e2e_steps, "host_buffers": "pinned (cnnacc_alloc_host)", "matches_device_run": ok},
+                    "batch": Be, "steps": e2e_steps, "host_buffers": "pinned (cnnacc_alloc_host)", "cpu_affinity": affinity, "matches_device_run": ok},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
