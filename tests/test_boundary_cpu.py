@@ -73,6 +73,8 @@ def test_window_plan_for_large_images(lib):
         owned = np.zeros(n_out, np.int32)
         for i in range(n):
             assert 0 <= g[i] <= n_out - 16 and s[i] < e[i]
+            if n_out % 2 == 0:                       # H, W are multiples of 16, so n_out is even in practice: even window
+                assert g[i] % 2 == 0                 # origins keep the TMA box's x coordinate 16-byte aligned (8*g - 16)
             for o in range(s[i], e[i]):
                 loc = o - g[i]
                 assert 0 <= loc <= 15 and (loc >= 1 or g[i] == 0) and (loc <= 14 or g[i] == n_out - 16)
