@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("CNNACC_LIB_PATH") or os.path.join(_DIR, "libcnnacc.so
 CSRC = os.path.join(_DIR, "csrc")
 
 OK, ERR_TIMEOUT, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
-FLAG_DEVICE_PTRS, FLAG_DIRECT, FLAG_KEEP_MAPS, FLAG_CLS_GIVEN, FLAG_BBOX_UPSAMPLED = 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_DEVICE_PTRS, FLAG_DIRECT, FLAG_KEEP_MAPS, FLAG_CLS_GIVEN, FLAG_BBOX_UPSAMPLED, FLAG_LOGITS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 
 # every symbol include/cnnacc.h declares: name -> (restype, argtypes)
 _c = ctypes
@@ -23,6 +23,8 @@ SYMBOLS = {
     "cnnacc_load_weights": (_c.c_int, [_H, _c.c_void_p, _c.c_size_t]),
     "cnnacc_set_shifts": (_c.c_int, [_H, _c.c_int, _c.c_int, _c.c_int]),
     "cnnacc_get_shifts": (_c.c_int, [_H, _c.POINTER(_c.c_int)]),
+    "cnnacc_set_accumulator_bits": (_c.c_int, [_H, _c.c_int]),
+    "cnnacc_get_accumulator_bits": (_c.c_int, [_H]),
     "cnnacc_pack_weights_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "cnnacc_tile_plan_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "cnnacc_run_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
@@ -43,6 +45,9 @@ SYMBOLS = {
                                         _c.c_void_p, _c.c_uint32]),
     "cnnacc_alloc_host": (_c.c_int, [_c.c_size_t, _c.POINTER(_c.c_void_p)]),
     "cnnacc_free_host": (_c.c_int, [_c.c_void_p]),
+    "cnnacc_register_host": (_c.c_int, [_c.c_void_p, _c.c_size_t]),
+    "cnnacc_unregister_host": (_c.c_int, [_c.c_void_p]),
+    "cnnacc_probe_int8_peak": (_c.c_int, [_H, _c.c_double, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double)]),
     "cnnacc_timer_start": (_c.c_int, [_H]),
     "cnnacc_timer_stop": (_c.c_int, [_H, _c.POINTER(_c.c_float)]),
     "cnnacc_synchronize": (_c.c_int, [_H]),

@@ -13,6 +13,7 @@ Same call surface as the reference (file:line under /root/reference/software/):
 plus the batch entry points the reference has no analogue for: run_batch, classify_batch, infer_batch.
 There is no CPU fallback and no simulation mode: without the CUDA library / a B200 the constructor raises.
 """
+import contextlib
 import ctypes
 import os
 import time
@@ -38,6 +39,15 @@ def _is_torch_cuda(x):
 
 def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def register_host(array):
+    """Page-lock a host array the caller owns (e.g. an np.memmap of a /dev/shm file shared by the per-GPU processes) so the
+    copy engines can write into it directly.  Returns a callable that unregisters it."""
+    lib = _lib.load()
+    a = np.asarray(array)
+    _lib.check(lib.cnnacc_register_host(ctypes.c_void_p(a.ctypes.data), a.nbytes))
+    return lambda: lib.cnnacc_unregister_host(ctypes.c_void_p(a.ctypes.data))
 
 
 def alloc_host(shape, dtype=np.uint8):
@@ -66,6 +76,7 @@ class CNNAccelerator:
         self._out_ch = 0
         self._out_addr = 0
         self._n_cls = 0
+        self._user_stream = 0
         self._finalizer = weakref.finalize(self, self._libc.cnnacc_destroy, self._h)
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -81,7 +92,27 @@ class CNNAccelerator:
 
     def use_stream(self, cuda_stream_ptr):
         """Launch on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = own stream."""
-        self._check(self._libc.cnnacc_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+        self._user_stream = int(cuda_stream_ptr or 0)
+        self._check(self._libc.cnnacc_set_stream(self._h, ctypes.c_void_p(self._user_stream)))
+
+    @contextlib.contextmanager
+    def _on_stream_of(self, *tensors):
+        """Device-pointer calls are asynchronous.  Unless the caller chose a stream with use_stream(), run them on torch's
+        CURRENT stream of the tensors' device, so they are ordered after the ops that produced the inputs and before the ops
+        that consume the outputs (a `.cpu()` right after the call is then safe)."""
+        import torch
+        for t in tensors:
+            if t is not None and t.get_device() != self.device:
+                raise ValueError(f"tensor is on cuda:{t.get_device()}, this accelerator is on cuda:{self.device}")
+        if self._user_stream:
+            yield
+            return
+        ptr = torch.cuda.current_stream(self.device).cuda_stream or 1       # 0 = legacy default stream = cudaStreamLegacy (0x1)
+        self._check(self._libc.cnnacc_set_stream(self._h, ctypes.c_void_p(ptr)))
+        try:
+            yield
+        finally:
+            self._check(self._libc.cnnacc_set_stream(self._h, ctypes.c_void_p(0)))
 
     def synchronize(self):
         self._check(self._libc.cnnacc_synchronize(self._h))
@@ -118,6 +149,20 @@ class CNNAccelerator:
         s = (ctypes.c_int * 3)()
         self._check(self._libc.cnnacc_get_shifts(self._h, s))
         return tuple(s)
+
+    def set_accumulator_bits(self, bits=32):
+        """32 = arm_cnn.c's int32 accumulator (default, the parity target); 24 = the PL accumulator / the trainer's bit-accurate
+        model (rtl/core/accumulator.v:15, training/train_cnn.py:101-116): sums wrap to 24-bit two's complement before the pool."""
+        self._check(self._libc.cnnacc_set_accumulator_bits(self._h, int(bits)))
+
+    def get_accumulator_bits(self):
+        return int(self._libc.cnnacc_get_accumulator_bits(self._h))
+
+    def probe_int8_peak(self, target_ms=50.0):
+        """Dense int8 tensor-core ceiling of this GPU measured now (tcgen05.mma kind::i8 N=256 on every SM) -> (TOP/s, ms)."""
+        tops, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(self._libc.cnnacc_probe_int8_peak(self._h, float(target_ms), ctypes.byref(tops), ctypes.byref(ms)))
+        return tops.value, ms.value
 
     def start_inference(self):
         """pynq_inference.py:231-234."""
@@ -181,8 +226,11 @@ class CNNAccelerator:
             n, H, W = images.shape
             if out is None:
                 out = torch.empty((n, 64, H // 8, W // 8), dtype=torch.uint8, device=images.device)
-            self._check(self._libc.cnnacc_run_batch(self._h, ctypes.c_void_p(images.data_ptr()), n, H, W,
-                                                    ctypes.c_void_p(out.data_ptr()), flags | _lib.FLAG_DEVICE_PTRS))
+            elif not (_is_torch_cuda(out) and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n * 64 * (H // 8) * (W // 8)):
+                raise ValueError("out must be a contiguous CUDA uint8 tensor of n*64*(H/8)*(W/8) elements")
+            with self._on_stream_of(images, out):
+                self._check(self._libc.cnnacc_run_batch(self._h, ctypes.c_void_p(images.data_ptr()), n, H, W,
+                                                        ctypes.c_void_p(out.data_ptr()), flags | _lib.FLAG_DEVICE_PTRS))
             return out
         images = np.ascontiguousarray(images, dtype=np.uint8)
         if images.ndim != 3:
@@ -201,21 +249,26 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_load_classifier(self._h, _vp(fc_w), _vp(fc_b), fc_w.shape[0]))
         self._n_cls = fc_w.shape[0]
 
-    def _predict(self, fn, x, direct=False, bbox="vec"):
+    def _predict(self, fn, x, direct=False, bbox="vec", logits=False):
         if bbox not in ("vec", "upsampled"):
             raise ValueError("bbox must be 'vec' (realtime_detect.bbox_vec) or 'upsampled' (Classifier.get_cam_bbox)")
-        flags = (_lib.FLAG_DIRECT if direct else 0) | (_lib.FLAG_BBOX_UPSAMPLED if bbox == "upsampled" else 0)
+        flags = (_lib.FLAG_DIRECT if direct else 0) | (_lib.FLAG_BBOX_UPSAMPLED if bbox == "upsampled" else 0) | \
+                (_lib.FLAG_LOGITS if logits else 0)
         if self._n_cls == 0:
             raise RuntimeError("classifier not loaded")
         if _is_torch_cuda(x):
             import torch
+            # the kernels read each item through 128-bit loads / a TMA box: shape, dtype and layout must be exact
+            if x.dtype != torch.uint8 or not x.is_contiguous() or x.dim() < 2 or x[0].numel() != 16384:
+                raise ValueError("expected a contiguous CUDA uint8 tensor of [N,128,128] images or [N,64,256] features")
             n = x.shape[0]
             probs = torch.empty((n, self._n_cls), dtype=torch.float32, device=x.device)
             cls = torch.empty((n,), dtype=torch.int32, device=x.device)
             bbox = torch.empty((n, 4), dtype=torch.int32, device=x.device)
-            self._check(fn(self._h, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(probs.data_ptr()),
-                           ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(bbox.data_ptr()),
-                           flags | _lib.FLAG_DEVICE_PTRS))
+            with self._on_stream_of(x):
+                self._check(fn(self._h, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(probs.data_ptr()),
+                               ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(bbox.data_ptr()),
+                               flags | _lib.FLAG_DEVICE_PTRS))
             return cls, probs, bbox
         x = np.ascontiguousarray(x, dtype=np.uint8)
         n = x.shape[0]
@@ -227,10 +280,11 @@ class CNNAccelerator:
         self._check(fn(self._h, _vp(x), n, _vp(probs), _vp(cls), _vp(bbox), flags))
         return cls, probs, bbox
 
-    def classify_batch(self, features, bbox="vec"):
+    def classify_batch(self, features, bbox="vec", logits=False):
         """features [N,64,256] (or [N,64,16,16]) u8 -> (cls [N] i32, probs [N,n_cls] f32, bbox [N,4] i32).
-        bbox='vec': realtime_detect.bbox_vec; bbox='upsampled': pynq_inference.Classifier.get_cam_bbox."""
-        return self._predict(self._libc.cnnacc_classify_batch, features, bbox=bbox)
+        bbox='vec': realtime_detect.bbox_vec; bbox='upsampled': pynq_inference.Classifier.get_cam_bbox.
+        logits=True: the second element holds the raw logits W.pooled + b (realtime_detect.py:79) instead of the softmax."""
+        return self._predict(self._libc.cnnacc_classify_batch, features, bbox=bbox, logits=logits)
 
     def pool_features(self, features):
         """features [N,64,256] u8 -> [N,1024] f32 spatial-bin pooled, /255 (retrain_classifier.py:188-205): the trainer's input."""
@@ -270,9 +324,10 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_classify_batch(self._h, _vp(x), n, None, _vp(cls), _vp(bbox), _lib.FLAG_CLS_GIVEN))
         return bbox
 
-    def infer_batch(self, images, direct=False, bbox="vec"):
-        """images [N,128,128] u8 -> (cls, probs, bbox); features never leave the GPU."""
-        return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox)
+    def infer_batch(self, images, direct=False, bbox="vec", logits=False):
+        """images [N,128,128] u8 -> (cls, probs, bbox).  The classifier / CAM-box tail runs inside the conv-stack kernel on
+        the feature map still in shared memory: only 44 B of predictions per image reach HBM."""
+        return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox, logits)
 
     def preprocess(self, frames):
         """realtime_detect.py:582-591 for a batch: frames [N,h,w,3] u8 BGR -> [N,128,128] u8 (centre-crop, BGR2GRAY,
@@ -283,8 +338,9 @@ class CNNAccelerator:
                 raise ValueError("expected a contiguous [N,h,w,3] uint8 tensor")
             n, fh, fw = frames.shape[:3]
             out = torch.empty((n, 128, 128), dtype=torch.uint8, device=frames.device)
-            self._check(self._libc.cnnacc_preprocess_bgr(self._h, ctypes.c_void_p(frames.data_ptr()), n, fh, fw,
-                                                         ctypes.c_void_p(out.data_ptr()), _lib.FLAG_DEVICE_PTRS))
+            with self._on_stream_of(frames):
+                self._check(self._libc.cnnacc_preprocess_bgr(self._h, ctypes.c_void_p(frames.data_ptr()), n, fh, fw,
+                                                             ctypes.c_void_p(out.data_ptr()), _lib.FLAG_DEVICE_PTRS))
             return out
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         if frames.ndim != 4 or frames.shape[3] != 3:

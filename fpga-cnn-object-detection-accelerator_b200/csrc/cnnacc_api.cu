@@ -9,15 +9,9 @@
 #include <string>
 
 #include "conv_direct.cuh"
-#if defined(CNNACC_EXPERIMENT_V9)      // tools/experiments: all three layers on tcgen05 (not the product)
-#include "../../tools/experiments/conv_fused_v9.cuh"
-#define CNNACC_EXPERIMENT_V8 1
-#elif defined(CNNACC_EXPERIMENT_V8)
-#include "../../tools/experiments/conv_fused_v8.cuh"
-#else
 #include "conv_fused.cuh"
-#endif
 #include "tail.cuh"
+#include "int8_peak_probe.cuh"
 #include "cam_upsampled.cuh"
 #include "preprocess.cuh"
 #include "tiling.cuh"
@@ -49,8 +43,9 @@ struct cnnacc_handle {
     cudaStream_t st_h2d = nullptr, st_k = nullptr, st_d2h = nullptr;   // one stream per engine for host-pointer batches
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_done = nullptr;
     int sm_count = 0;
-    bool weights_loaded = false, fc_loaded = false;
+    bool weights_loaded = false, fc_loaded = false, tail_attr_set = false;
     int shifts[3] = {2, 4, 6};                  // SHIFT_L0..2 defaults, pynq_inference.py:83-85
+    bool acc24 = false;                         // accumulator width: false = int32 (arm_cnn.c:31), true = 24-bit wrap (accumulator.v:15)
     uint8_t wbin[CNNACC_WEIGHT_BYTES];
     // device-side weights
     uint32_t* d_wdirect = nullptr; size_t wdirect_off[3] = {0, 0, 0};
@@ -111,10 +106,12 @@ bool tiled_ok(const cnnacc_handle* h, int H, int W, uint32_t flags) {
 int launch_direct_layer(cnnacc_handle* h, cudaStream_t stream, int layer, const uint8_t* in, uint8_t* out,
                         int64_t n, int H, int W) {
     const int tiles_x = (W + kDirTile - 1) / kDirTile, tiles_y = (H + kDirTile - 1) / kDirTile;
-    dim3 grid((unsigned)n, (unsigned)(tiles_x * tiles_y), (unsigned)(kLayers[layer].oc / kDirOcb));
+    // image and tile share gridDim.x (2^31-1); gridDim.y (65535) would overflow at 8192x8192 (256 x 256 layer-0 tiles)
+    if (n * tiles_x * tiles_y > 0x7fffffffLL) return fail(h, CNNACC_ERR_ARG, "too many tiles in one launch");
+    dim3 grid((unsigned)(n * tiles_x * tiles_y), 1u, (unsigned)(kLayers[layer].oc / kDirOcb));
     conv3x3_pool_direct_kernel<<<grid, 256, 0, stream>>>(in, out, h->d_wdirect + h->wdirect_off[layer],
                                                          kLayers[layer].ic, kLayers[layer].oc, H, W,
-                                                         h->shifts[layer], tiles_x);
+                                                         h->shifts[layer], tiles_x, tiles_x * tiles_y, h->acc24 ? 1 : 0);
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
@@ -176,14 +173,48 @@ int ensure_maps(cnnacc_handle* h, int64_t n, int H, int W) {
     return 0;
 }
 
-int launch_tail(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, int64_t n, float* d_probs,
-                int32_t* d_cls, int32_t* d_bbox, bool cls_given = false) {
+TailArgs make_tail(const cnnacc_handle* h, float* d_probs, int32_t* d_cls, int32_t* d_bbox, bool cls_given, uint32_t flags) {
+    TailArgs A;
+    A.fc_w = h->d_fcw; A.fc_b = h->d_fcb; A.n_cls = h->n_cls;
+    A.want_logits = (flags & CNNACC_FLAG_LOGITS) ? 1 : 0;
+    A.probs = d_probs; A.bbox_out = d_bbox;
+    A.cls_out = cls_given ? nullptr : d_cls;
+    A.cls_in = cls_given ? d_cls : nullptr;
+    return A;
+}
+
+// classify_vec + bbox_vec on n device-resident feature maps (tail.cuh)
+int launch_tail(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, int64_t n, const TailArgs& A) {
     if (n == 0) return 0;
-    classify_bbox_kernel<<<(unsigned)n, 256, 0, stream>>>(d_feats, h->d_fcw, h->d_fcb, h->n_cls, d_probs, d_cls, d_bbox,
-                                                          cls_given ? d_cls : nullptr);
+    if (!h->tail_attr_set) {
+        CU(h, cudaFuncSetAttribute(classify_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
+        h->tail_attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>((n + kTailGroups - 1) / kTailGroups, h->sm_count);
+    classify_bbox_kernel<<<grid, kTailGroups * kTailThreads, kTailSmem, stream>>>(d_feats, (long long)n, A);
     h->launches++;
     CU(h, cudaGetLastError());
     return 0;
+}
+
+// Conv stack + tail for m device-resident 128x128 images on `stream`.  The fused kernel's tail warps produce the
+// predictions while the features are still in shared memory; d_feat_ws (m x 16 KiB) is written only when the caller needs
+// the features afterwards (want_feats) or the per-layer kernels are in use.
+int infer_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_imgs, int64_t m, uint8_t* d_feat_ws, bool want_feats,
+                 const TailArgs& A, uint32_t flags) {
+    const bool fused_ok = !(flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS)) && h->fused.ready;
+    if (fused_ok) {
+        int rc = launch_fused(h->fused, stream, d_imgs, m, want_feats ? d_feat_ws : nullptr, h->shifts, h->sm_count, nullptr, nullptr, &A);
+        h->launches++;
+        if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+        return 0;
+    }
+    int rc;
+    if ((rc = conv_stack_device(h, stream, d_imgs, m, CNNACC_IMG, CNNACC_IMG, d_feat_ws, flags, h->d_l0, h->d_l1))) return rc;
+    return launch_tail(h, stream, d_feat_ws, m, A);
+}
+bool infer_needs_feat_ws(const cnnacc_handle* h, bool want_feats, uint32_t flags) {
+    return want_feats || (flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS)) || !h->fused.ready;
 }
 
 // Classifier.get_cam_bbox per image (cam_upsampled.cuh); d_cam may be null
@@ -375,15 +406,19 @@ int cnnacc_set_shifts(cnnacc_handle* h, int s0, int s1, int s2) {
     return CNNACC_OK;
 }
 
+int cnnacc_set_accumulator_bits(cnnacc_handle* h, int bits) {
+    if (!h) return CNNACC_ERR_ARG;
+    if (bits != 24 && bits != 32) return fail(h, CNNACC_ERR_ARG, "accumulator width must be 32 (arm_cnn.c) or 24 (RTL / train_cnn.py)");
+    h->acc24 = h->fused.acc24 = (bits == 24);
+    return CNNACC_OK;
+}
+
+int cnnacc_get_accumulator_bits(const cnnacc_handle* h) { return h ? (h->acc24 ? 24 : 32) : CNNACC_ERR_ARG; }
+
 int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint32_t* w0, uint8_t* b1, uint8_t* b2) {
     if (!weights_bin || !w0 || !b1 || !b2 || n != CNNACC_WEIGHT_BYTES) return CNNACC_ERR_ARG;
     static_assert(CNNACC_PACK_B1_BYTES == kB1Bytes && CNNACC_PACK_B2_BYTES == kB2Bytes, "header out of date");
-#ifdef CNNACC_EXPERIMENT_V8
-    (void)w0;
-    return CNNACC_ERR_STATE;                              // the experiment packs a different layer-0 operand
-#else
     fused_pack_weights(weights_bin, reinterpret_cast<uint32_t(*)[6]>(w0), reinterpret_cast<uint32_t(*)[32]>(w0 + 96), b1, b2);
-#endif
     return CNNACC_OK;
 }
 
@@ -624,7 +659,7 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     if (!h) return CNNACC_ERR_ARG;
     if (src_is_images && (rc = check_ready(h))) return rc;
     if (!h->fc_loaded) return fail(h, CNNACC_ERR_STATE, "classifier not loaded (call cnnacc_load_classifier)");
-    if (n < 0) return fail(h, CNNACC_ERR_ARG, "negative n");
+    if (n < 0 || n > 0x7fffffffLL) return fail(h, CNNACC_ERR_ARG, "n outside 0..2^31-1");
     if (n == 0) return CNNACC_OK;
     if (!src) return fail(h, CNNACC_ERR_ARG, "NULL input pointer");
     CU(h, cudaSetDevice(h->device));
@@ -633,26 +668,29 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     const bool maps = src_is_images && needs_maps(h, CNNACC_IMG, CNNACC_IMG, flags);
     const bool cls_given = (flags & CNNACC_FLAG_CLS_GIVEN) != 0;
     if (cls_given && !cls) return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_CLS_GIVEN without a cls array");
-    const bool upsampled = (flags & CNNACC_FLAG_BBOX_UPSAMPLED) != 0;
-    if (upsampled && bbox && !cls && (flags & CNNACC_FLAG_DEVICE_PTRS))
+    const bool upsampled = (flags & CNNACC_FLAG_BBOX_UPSAMPLED) != 0 && bbox;
+    if (upsampled && !cls && (flags & CNNACC_FLAG_DEVICE_PTRS))
         return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_BBOX_UPSAMPLED with device pointers needs a cls array");
+    // images in: does anything after the conv stack need the feature maps in HBM?
+    const bool feat_ws = src_is_images && infer_needs_feat_ws(h, upsampled, flags);
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
-        const int64_t chunk = std::min<int64_t>(n, 16384);
-        if (src_is_images) {
+        // one fused launch covers the whole call unless a workspace bounds the chunk
+        const int64_t chunk = feat_ws ? std::min<int64_t>(n, 16384) : n;
+        if (feat_ws) {
             if ((rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)chunk * img_sz))) return rc;
             if (maps && (rc = ensure_maps(h, chunk, CNNACC_IMG, CNNACC_IMG))) return rc;
         }
         for (int64_t i0 = 0; i0 < n; i0 += chunk) {
             const int64_t m = std::min(chunk, n - i0);
+            const TailArgs A = make_tail(h, probs ? probs + i0 * nc : nullptr, cls ? cls + i0 : nullptr,
+                                         (bbox && !upsampled) ? bbox + i0 * 4 : nullptr, cls_given, flags);
             const uint8_t* f = src + i0 * img_sz;
             if (src_is_images) {
-                if ((rc = conv_stack_device(h, h->stream, src + i0 * img_sz, m, CNNACC_IMG, CNNACC_IMG, h->d_feat, flags, h->d_l0, h->d_l1))) return rc;
+                if ((rc = infer_device(h, h->stream, f, m, h->d_feat, upsampled, A, flags))) return rc;
                 f = h->d_feat;
-            }
-            if ((rc = launch_tail(h, h->stream, f, m, probs ? probs + i0 * nc : nullptr, cls ? cls + i0 : nullptr,
-                                  (bbox && !upsampled) ? bbox + i0 * 4 : nullptr, cls_given))) return rc;
-            if (bbox && upsampled && (rc = launch_cam_upsampled(h, h->stream, f, m, cls + i0, bbox + i0 * 4, nullptr))) return rc;
+            } else if ((rc = launch_tail(h, h->stream, f, m, A))) return rc;
+            if (upsampled && (rc = launch_cam_upsampled(h, h->stream, f, m, cls + i0, bbox + i0 * 4, nullptr))) return rc;
         }
         return CNNACC_OK;
     }
@@ -662,42 +700,45 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     if (n <= kSmallN) {                                      // latency path: one stream, one result copy
         Slot& s = h->slots[0];
         cudaStream_t st = h->st_k;
-        if ((rc = slot_reserve(h, s, n * img_sz, src_is_images ? n * img_sz : 0, 0))) return rc;
+        if ((rc = slot_reserve(h, s, n * img_sz, feat_ws ? n * img_sz : 0, 0))) return rc;
         if (maps && (rc = ensure_maps(h, n, CNNACC_IMG, CNNACC_IMG))) return rc;
         const SmallPred p = small_pred(h, n);
         CU(h, cudaMemcpyAsync(s.d_in, src, n * img_sz, cudaMemcpyHostToDevice, st));
         if (cls_given) CU(h, cudaMemcpyAsync(p.d_cls, cls, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        const TailArgs A = make_tail(h, p.d_probs, p.d_cls, upsampled ? nullptr : p.d_bbox, cls_given, flags);
         const uint8_t* f = s.d_in;
         if (src_is_images) {
-            if ((rc = conv_stack_device(h, st, s.d_in, n, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+            if ((rc = infer_device(h, st, s.d_in, n, s.d_out, upsampled, A, flags))) return rc;
             f = s.d_out;
-        }
-        if ((rc = launch_tail(h, st, f, n, p.d_probs, p.d_cls, upsampled ? nullptr : p.d_bbox, cls_given))) return rc;
-        if (bbox && upsampled && (rc = launch_cam_upsampled(h, st, f, n, p.d_cls, p.d_bbox, nullptr))) return rc;
+        } else if ((rc = launch_tail(h, st, f, n, A))) return rc;
+        if (upsampled && (rc = launch_cam_upsampled(h, st, f, n, p.d_cls, p.d_bbox, nullptr))) return rc;
         CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         small_pred_unpack(h, p, n, probs, cls, bbox, cls_given);
         return src_is_images ? check_fused_status(h) : CNNACC_OK;
     }
-    const int64_t hchunk = std::min<int64_t>(n, 4096);
+    // Same ring as cnnacc_run_batch's host path; only the predictions (44 B per image) come back, so the link carries
+    // H2D traffic alone and the chunks can be a quarter of the call, clamped to 4..32 MiB.
+    const size_t chunk_bytes = std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * img_sz / 4));
+    const int64_t hchunk = std::min<int64_t>(n, (int64_t)(chunk_bytes / img_sz));
     if (maps && (rc = ensure_maps(h, hchunk, CNNACC_IMG, CNNACC_IMG))) return rc;
     int64_t ci = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
+    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
         const int64_t m = std::min(hchunk, n - i0);
         Slot& s = h->slots[ci % kSlots];
-        if ((rc = slot_reserve(h, s, hchunk * img_sz, src_is_images ? hchunk * img_sz : 0, hchunk))) return rc;
+        if ((rc = slot_reserve(h, s, hchunk * img_sz, feat_ws ? hchunk * img_sz : 0, hchunk))) return rc;
         if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
         CU(h, cudaMemcpyAsync(s.d_in, src + i0 * img_sz, m * img_sz, cudaMemcpyHostToDevice, h->st_h2d));
         if (cls_given) CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_h2d));
         CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
         CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        const TailArgs A = make_tail(h, s.d_probs, s.d_cls, upsampled ? nullptr : s.d_bbox, cls_given, flags);
         const uint8_t* f = s.d_in;
         if (src_is_images) {
-            if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, CNNACC_IMG, CNNACC_IMG, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+            if ((rc = infer_device(h, h->st_k, s.d_in, m, s.d_out, upsampled, A, flags))) return rc;
             f = s.d_out;
-        }
-        if ((rc = launch_tail(h, h->st_k, f, m, s.d_probs, s.d_cls, upsampled ? nullptr : s.d_bbox, cls_given))) return rc;
-        if (bbox && upsampled && (rc = launch_cam_upsampled(h, h->st_k, f, m, s.d_cls, s.d_bbox, nullptr))) return rc;
+        } else if ((rc = launch_tail(h, h->st_k, f, m, A))) return rc;
+        if (upsampled && (rc = launch_cam_upsampled(h, h->st_k, f, m, s.d_cls, s.d_bbox, nullptr))) return rc;
         CU(h, cudaEventRecord(s.ev_k, h->st_k));
         CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
         if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
@@ -706,7 +747,7 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
         CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
-    return CNNACC_OK;
+    return src_is_images ? check_fused_status(h) : CNNACC_OK;
 }
 
 int cnnacc_classify_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
@@ -810,10 +851,11 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
     const bool upsampled = (flags & CNNACC_FLAG_BBOX_UPSAMPLED) != 0;
     auto tail = [&](cudaStream_t st, const uint8_t* d_gray, int64_t m, float* d_probs, int32_t* d_cls, int32_t* d_bbox) -> int {
         int r;
-        if ((r = grow(h, &h->d_feat, &h->cap_feat, (size_t)m * img_sz))) return r;
-        if ((r = conv_stack_device(h, st, d_gray, m, CNNACC_IMG, CNNACC_IMG, h->d_feat, 0, h->d_l0, h->d_l1))) return r;
-        if ((r = launch_tail(h, st, h->d_feat, m, d_probs, d_cls, upsampled ? nullptr : d_bbox))) return r;
-        if (upsampled && d_bbox && (r = launch_cam_upsampled(h, st, h->d_feat, m, d_cls, d_bbox, nullptr))) return r;
+        const bool ups = upsampled && d_bbox;
+        if (infer_needs_feat_ws(h, ups, 0) && (r = grow(h, &h->d_feat, &h->cap_feat, (size_t)m * img_sz))) return r;
+        const TailArgs A = make_tail(h, d_probs, d_cls, ups ? nullptr : d_bbox, false, flags);
+        if ((r = infer_device(h, st, d_gray, m, h->d_feat, ups, A, 0))) return r;
+        if (ups && (r = launch_cam_upsampled(h, st, h->d_feat, m, d_cls, d_bbox, nullptr))) return r;
         return 0;
     };
 
@@ -849,7 +891,6 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
     }
     // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)16 << 20) / frame_sz)));
-    if (detect && (rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)hchunk * img_sz))) return rc;
     int64_t ci = 0;
     for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
         const int64_t m = std::min(hchunk, n - i0);
@@ -882,6 +923,50 @@ int cnnacc_preprocess_bgr(cnnacc_handle* h, const uint8_t* frames, int64_t n, in
 int cnnacc_detect_frames(cnnacc_handle* h, const uint8_t* frames, int64_t n, int fh, int fw, uint8_t* gray128,
                          float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
     return frames_impl(h, frames, n, fh, fw, gray128, probs, cls, bbox, true, flags);
+}
+
+int cnnacc_probe_int8_peak(cnnacc_handle* h, double target_ms, double* tops, double* ms_out) {
+    if (!h || !tops) return fail(h, CNNACC_ERR_ARG, "NULL argument");
+    if (!(target_ms > 0.0) || target_ms > 2000.0) return fail(h, CNNACC_ERR_ARG, "target_ms outside (0, 2000]");
+    CU(h, cudaSetDevice(h->device));
+    int* d_status = nullptr;
+    CU(h, cudaMalloc(&d_status, sizeof(int)));
+    CU(h, cudaMemset(d_status, 0, sizeof(int)));
+    auto run = [&](int iters, float* ms) -> int {
+        CU(h, cudaEventRecord(h->ev_a, h->stream));
+        int8_peak_probe_kernel<<<h->sm_count, 32, kProbeSmem, h->stream>>>(iters, d_status);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        CU(h, cudaEventRecord(h->ev_b, h->stream));
+        CU(h, cudaEventSynchronize(h->ev_b));
+        CU(h, cudaEventElapsedTime(ms, h->ev_a, h->ev_b));
+        return 0;
+    };
+    int rc; float ms = 0.f;
+    const int iters0 = 1 << 15;                                          // calibration: ~2 ms
+    if ((rc = run(iters0, &ms)) || (rc = run(iters0, &ms))) { cudaFree(d_status); return rc; }
+    double want = (double)iters0 * target_ms / std::max(ms, 1e-3f);
+    const int iters = (int)std::min<double>(1 << 30, std::max<double>(iters0, want)) & ~7;
+    if ((rc = run(iters, &ms))) { cudaFree(d_status); return rc; }
+    int st = 0;
+    CU(h, cudaMemcpy(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_status);
+    if (st) return fail(h, CNNACC_ERR_CUDA, "int8 peak probe timed out");
+    *tops = (double)h->sm_count * iters * kProbeOpsPerMma / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return CNNACC_OK;
+}
+
+int cnnacc_register_host(void* p, size_t bytes) {
+    if (!p || bytes == 0) return CNNACC_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return CNNACC_ERR_CUDA; }
+    return CNNACC_OK;
+}
+
+int cnnacc_unregister_host(void* p) {
+    if (!p) return CNNACC_ERR_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? CNNACC_OK : CNNACC_ERR_CUDA;
 }
 
 int cnnacc_alloc_host(size_t bytes, void** out) {

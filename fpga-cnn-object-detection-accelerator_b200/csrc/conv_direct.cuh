@@ -30,13 +30,14 @@ constexpr int kDirWPerOI = 8;                // packed words per (oc, ic): lo[3]
 __global__ void __launch_bounds__(256)
 conv3x3_pool_direct_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                            const uint32_t* __restrict__ wpk, int ic, int oc, int H, int W, int shift,
-                           int tiles_x)
+                           int tiles_x, int tiles_per_img, int acc24)
 {
     __shared__ uint32_t s_tile[kDirIcc][kDirRows][kDirPitchW];
     __shared__ uint4    s_w[kDirIcc][kDirOcb][2];
 
-    const int img   = blockIdx.x;
-    const int tileY = blockIdx.y / tiles_x, tileX = blockIdx.y % tiles_x;
+    // image and tile share gridDim.x: gridDim.y's 65535 limit is below the 256 x 256 layer-0 tiles of an 8192 x 8192 image
+    const int img   = blockIdx.x / tiles_per_img, tile = blockIdx.x % tiles_per_img;
+    const int tileY = tile / tiles_x, tileX = tile % tiles_x;
     const int ocg   = blockIdx.z;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int x0 = tileX * kDirTile, y0 = tileY * kDirTile;
@@ -100,6 +101,10 @@ conv3x3_pool_direct_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__
         uint8_t* o_img = out + (size_t)img * oc * oH * oW;
 #pragma unroll
         for (int o = 0; o < kDirOcb; o++) {
+            if (acc24) {     // RTL / trainer accumulator: 24-bit two's complement wrap of every sum BEFORE the pool
+#pragma unroll               // (accumulator.v:15, train_cnn.py:110-111); wrapping once at the end equals wrapping every add
+                for (int q = 0; q < 4; q++) acc[o][q] = (int)((unsigned)acc[o][q] << 8) >> 8;
+            }
             int m = max4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
             m = min(max(m, 0) >> shift, 255);
             o_img[((size_t)(ocg * kDirOcb + o) * oH + py) * oW + px] = (uint8_t)m;

@@ -35,11 +35,14 @@
 //   warps 16-19  epilogues : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
 //   warp 20      tcgen05 MMA issue (whole warp walks the schedule, one elected lane issues), TMEM allocation,
 //                TMA loads (weights once, then images two ahead)
+//   warps 21-22  (kTail instantiation only) the classifier / CAM-box tail of tail.cuh on the layer-2 staging buffer of the
+//                image the epilogue warps have just finished: predictions leave the SM, the feature map need not
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tail.cuh"
 #include "weights_pack.h"
 
 namespace cnnacc {
@@ -71,13 +74,20 @@ constexpr int kOffB1    = kOffA2 + kA2Bytes;          // 148480
 constexpr int kOffB2    = kOffB1 + kB1Bytes;          // 181248
 constexpr int kOffStage = kOffB2 + kB2Bytes;          // 199680
 constexpr int kOffBar   = kOffStage + kStageBytes;    // 216064
-constexpr int kFusedSmem = kOffBar + 256;             // 216320 <= 232448
+constexpr int kOffTail  = kOffBar + 256;              // scratch of the two tail warps (tail.cuh)
+#ifdef CNNACC_TRACE
+constexpr int kTailWRows = 2;                         // the trace build's static buffers take 4 KiB
+#else
+constexpr int kTailWRows = 3;                         // classifier rows kept in shared memory (the rest: __ldg through L1)
+#endif
+constexpr int kOffTailW = kOffTail + kTailScratchBytes;
+constexpr int kFusedSmem = kOffTailW + kTailWRows * 4096;   // 229888 <= 232448
 
 // Optional schedule trace (tools only, -DCNNACC_TRACE): CTA 0 records clock() at pipeline events in shared memory and
 // prints them at exit (tools/trace_run.py).
 #ifdef CNNACC_TRACE
 #include <cstdio>
-constexpr int kTraceMax = 200, kTraceRoles = 4;
+constexpr int kTraceMax = 110, kTraceRoles = 5;
 #define TRACE(role, code)                                                                                          \
     do {                                                                                                           \
         if (blockIdx.x == 0 && lane == 0 && trace_n < kTraceMax) {                                                 \
@@ -110,8 +120,13 @@ constexpr int kL0Dp4aWarps = CNNACC_L0_DP4A_WARPS;
 constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
 static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
 constexpr int kWarpMma = kL0Warps + kEpiWarps;       // the last warp: MMA issue and TMA loads
-constexpr int kFusedThreads = (kWarpMma + 1) * 32;    // 21 warps = 672: leaves 96 registers per thread
+constexpr int kFusedThreads = (kWarpMma + 1) * 32;    // 21 warps = 672
+constexpr int kTailWarps = kTailThreads / 32;         // + 2 warps in the kTail instantiation: 23 warps, still <= 6 per sub-partition
 constexpr uint32_t kTmemCols = 512;
+#ifndef CNNACC_WAIT_BUDGET_CLK
+#define CNNACC_WAIT_BUDGET_CLK 8000000000LL            // bounded pipeline waits: ~4 s of SM clocks
+#endif
+constexpr long long kWaitBudgetClk = CNNACC_WAIT_BUDGET_CLK;
 
 // mbarrier slots (8 bytes each) at kOffBar
 enum : uint32_t {
@@ -121,21 +136,25 @@ enum : uint32_t {
     kBarTmFull0, kBarTmFull1, kBarTmEmpty0, kBarTmEmpty1,           // MMA -> epilogue ; epilogue -> MMA (TMEM halves)
     kBarA2ReadyA, kBarA2ReadyB,                                     // epilogue -> MMA: act2 written by tiles 0-6 (all block 0 needs) / by all 8
     kBarW,                                                          // weights landed
+    kBarStageFull, kBarStageFree,                                   // epilogue -> tail warps (features staged) ; tail -> epilogue
     kNumBars
 };
 
 // error bits reported through the status word
 constexpr int kErrInputTimeout = 1, kErrMmaTimeout = 2, kErrEmptyTimeout = 4, kErrWeightTimeout = 8,
-              kErrAct1Timeout = 16, kErrAct2Timeout = 32, kErrSlotTimeout = 64;
+              kErrAct1Timeout = 16, kErrAct2Timeout = 32, kErrSlotTimeout = 64, kErrStageTimeout = 128;
 
 struct FusedParams {
     uint32_t w0[16][6];          // layer-0 dp4a words per out-channel: lo[dy], hi[dy]  (constant bank; CNNACC_L0_DP4A build)
     uint32_t w0f[8][32];         // layer-0 mma.sync B fragments: [block = py*4 + ol][lane]
     int shift0, shift1, shift2;
+    int acc24;                   // layer-2 accumulators wrap at 24 bits before the pool (RTL / trainer width, accumulator.v:15,
+                                 // train_cnn.py:110-111); layers 0/1 cannot reach 2^23 (9*255*128, 16*9*255*128 = 4.7 M)
     int n_images;
     const uint8_t* b1;           // packed layer-1 B operand (kB1Bytes)
     const uint8_t* b2;           // packed layer-2 B operand (kB2Bytes)
-    uint8_t* out;                // [n][64][16][16]
+    uint8_t* out;                // [n][64][16][16]; may be null in the kTail instantiation (predictions only)
+    TailArgs tail;               // kTail instantiation: classifier + outputs (tail.cuh)
     uint8_t* dump_l0;            // optional [n][16][64][64]
     uint8_t* dump_l1;            // optional [n][32][32][32]
     int* status;                 // device int, OR-ed error bits
@@ -168,12 +187,14 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     return ok;
 }
-// Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.
+// Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.  Every try_wait parks the warp in
+// hardware for a while, and the clock is only consulted every 32 unsuccessful polls.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, long long budget) {
-    if (mbar_try(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        if (mbar_try(bar, parity)) return true;
+#pragma unroll 1
+        for (int i = 0; i < 32; i++)
+            if (mbar_try(bar, parity)) return true;
         if (clock64() - t0 > budget) return false;
     }
 }
@@ -246,14 +267,21 @@ __device__ __forceinline__ uint32_t act_u8(int v, int shift) {
     return d;
 }
 
+// 24-bit two's-complement wrap of a finished sum (accumulator.v:15 `reg signed [23:0]`; train_cnn.py:110-111
+// ((out + M) % 2M) - M): wrapping once at the end equals wrapping after every add.
+__device__ __forceinline__ int wrap24(int v) { return (int)((unsigned)v << 8) >> 8; }
+
 // ---- the kernel ---------------------------------------------------------------------------------------------
 // Register budget: each SM sub-partition has 16 384 registers and 21 warps put 6 on one of them, so 80 per thread
 // (6 x 80 x 32 = 15 360) is the most that launches; 96 would need <= 20 warps.
 // kWin = window mode (FusedParams::win_*): a separate instantiation, so the 128x128 path carries none of its code.
-template <bool kWin>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+// kTail = two more warps run the classifier / CAM-box tail on each image's staged features (tail.cuh).
+template <bool kWin, bool kTail>
+__global__ void __launch_bounds__(kFusedThreads + (kTail ? kTailThreads : 0), 1)
 conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FusedParams P)
 {
+    static_assert(!(kWin && kTail), "the tail needs a whole 16x16 map in the staging buffer");
+    constexpr int kThreads = kFusedThreads + (kTail ? kTailThreads : 0);
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bars = s_base + kOffBar;
@@ -272,7 +300,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 #endif
 
     // ---- one-time setup ---------------------------------------------------------------------------------
-    for (int i = tid; i < (kA1Alloc + kA2Bytes) / 16; i += kFusedThreads)                       // zero halos (and interiors)
+    for (int i = tid; i < (kA1Alloc + kA2Bytes) / 16; i += kThreads)                            // zero halos (and interiors)
         reinterpret_cast<uint4*>(smem + kOffA1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(bar(kBarInFull0), 1); mbar_init(bar(kBarInFull1), 1);
@@ -283,6 +311,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         mbar_init(bar(kBarTmEmpty0), kEpiWarps); mbar_init(bar(kBarTmEmpty1), kEpiWarps);
         mbar_init(bar(kBarA2ReadyA), kEpiWarps); mbar_init(bar(kBarA2ReadyB), kEpiWarps);
         mbar_init(bar(kBarW), 1);
+        mbar_init(bar(kBarStageFull), kEpiWarps); mbar_init(bar(kBarStageFree), kTailWarps);
         *s_err = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -298,8 +327,9 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
 
     auto wait_or_flag = [&](uint32_t b, uint32_t parity, int code) {
         if (mbar_try(b, parity)) return;                 // fast path: already complete
-        // ~0.1 s budget; once any wait has timed out every later wait gives up quickly so the CTA drains
-        if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : 200000000LL)) atomicOr(s_err, code);
+        // ~4 s budget (a wait this long means a broken pipeline, not time-slicing or a debugger); once any wait has timed
+        // out every later wait gives up quickly so the CTA drains.  A reported timeout invalidates the whole launch.
+        if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : kWaitBudgetClk)) atomicOr(s_err, code);
     };
 
     // TMA load of unit u (an image, or a window of a larger image) into an input slot; the box starts one pixel row above
@@ -520,9 +550,12 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 wrow = i >= (gy == 0 ? 0 : 1) && i <= (gy == P.win_ho - 16 ? 15 : 14);
                 wcs = (size_t)P.win_ho * P.win_wo;
                 wbase = P.out + ((size_t)(img / per) * 64 * P.win_ho + gy + i) * P.win_wo + wgx;
-            } else if (k > 0) {                          // the previous image's store must have finished reading staging
-                if (e == 0 && lane == 0) bulk_store_wait_read();
+            } else if (k > 0) {                          // the previous image's store and its tail must be done with staging
+                if (P.out && e == 0 && lane == 0) bulk_store_wait_read();
+                if (e == 0) TRACE(1, 70);
+                if constexpr (kTail) wait_or_flag(bar(kBarStageFree), (uint32_t)(k - 1) & 1, kErrStageTimeout);
                 epi_bar_sync();
+                if (e == 0) TRACE(1, 71);
             }
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
@@ -544,11 +577,19 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                         tmem_ld16(taddr, v0);
                         tmem_ld16(taddr + 64, v1);
                         tmem_ld_wait();
+                        if (P.acc24) {
+#pragma unroll
+                            for (int c = 0; c < 16; c++) { v0[c] = wrap24(v0[c]); v1[c] = wrap24(v1[c]); }
+                        }
 #pragma unroll
                         for (int c = 0; c < 16; c++) m[c] = max(v0[c], v1[c]);
                         tmem_ld16(taddr + 128, v0);
                         tmem_ld16(taddr + 192, v1);
                         tmem_ld_wait();
+                        if (P.acc24) {
+#pragma unroll
+                            for (int c = 0; c < 16; c++) { v0[c] = wrap24(v0[c]); v1[c] = wrap24(v1[c]); }
+                        }
 #pragma unroll
                         for (int c = 0; c < 16; c++) m[c] = max(m[c], max(v0[c], v1[c]));
                     }
@@ -571,9 +612,16 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 }
             }
             if (!win) {
-                fence_async_smem();
-                epi_bar_sync();
-                if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+                if constexpr (kTail) {                   // hand the staged map to the tail warps
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarStageFull));
+                    if (e == 0) TRACE(1, 72);
+                }
+                if (P.out) {
+                    fence_async_smem();
+                    epi_bar_sync();
+                    if (e == 0 && lane == 0) bulk_store(P.out + (size_t)img * 16384, s_base + kOffStage, kStageBytes);
+                }
             }
         }
         if (e == 0 && lane == 0) bulk_store_wait_all();
@@ -668,6 +716,21 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
         }
         TRACE_END(0);
+    } else if constexpr (kTail) {
+        // =============== tail warps: staged features -> class / probabilities / CAM box (tail.cuh) =================
+        const int T = (warp - kWarpMma - 1) * 32 + lane;
+        TailScratch* sc = reinterpret_cast<TailScratch*>(smem + kOffTail);
+        const TailWeights W = tail_stage_weights(reinterpret_cast<float*>(smem + kOffTailW), kTailWRows, P.tail, T);
+        tail_bar(2);
+        for (int k = 0; k < n_local; k++) {
+            const int img = (int)blockIdx.x + k * (int)gridDim.x;
+            wait_or_flag(bar(kBarStageFull), (uint32_t)k & 1, kErrStageTimeout);
+            tail_image(smem + kOffStage, sc, T, 2, P.tail, W, (size_t)img, [&] {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarStageFree));
+            }, [&](int code) { if (T == 0) TRACE(4, code); (void)code; });
+        }
+        if (T == 0) TRACE_END(4);
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------
@@ -698,6 +761,7 @@ struct FusedWeights {
     int* h_status = nullptr;      // mapped pinned mirror of the status word
     int* h_status_dev = nullptr;  // its device address
     bool attr_set = false;
+    bool acc24 = false;           // cnnacc_set_accumulator_bits(24)
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -776,8 +840,9 @@ inline int fused_load_weights(FusedWeights& fw, const uint8_t* wbin) {
     if ((e = cudaMemcpy(fw.d_b1, b1.data(), kB1Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpy(fw.d_b2, b2.data(), kB2Bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if (!fw.attr_set) {
-        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
-        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
+        if ((e = cudaFuncSetAttribute(conv_stack_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem)) != cudaSuccess) return (int)e;
         fw.attr_set = true;
     }
     if (!get_encode_tiled()) return (int)cudaErrorNotSupported;
@@ -811,8 +876,13 @@ struct FusedWindows {             // window mode: see FusedParams
     const short *gx = nullptr, *gy = nullptr;
 };
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
-                            const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr) {
+                            const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr,
+                            const TailArgs* tail = nullptr) {
     FusedParams P;
+    if (win && tail) return (int)cudaErrorInvalidValue;
+    if (!tail && !d_feats) return (int)cudaErrorInvalidValue;
+    std::memset(&P.tail, 0, sizeof(P.tail));
+    if (tail) P.tail = *tail;
     P.win_ntx = P.win_nty = P.win_ho = P.win_wo = 0;
     if (win) {
         if (win->ntx < 1 || win->nty < 1 || win->ntx > 80 || win->nty > 80) return (int)cudaErrorInvalidValue;
@@ -823,24 +893,26 @@ inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const C
     std::memcpy(P.w0, fw.w0, sizeof(P.w0));
     std::memcpy(P.w0f, fw.w0f, sizeof(P.w0f));
     P.shift0 = shifts[0]; P.shift1 = shifts[1]; P.shift2 = shifts[2];
+    P.acc24 = fw.acc24 ? 1 : 0;
     P.n_images = (int)n;
     P.b1 = fw.d_b1; P.b2 = fw.d_b2;
     P.out = d_feats; P.dump_l0 = dump_l0; P.dump_l1 = dump_l1;
     P.status = fw.d_status; P.status_host = fw.h_status_dev;
     const int grid = (int)std::min<int64_t>(n, sm_count);
-    if (win) conv_stack_fused_kernel<true><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
-    else     conv_stack_fused_kernel<false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    if (win)       conv_stack_fused_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    else if (tail) conv_stack_fused_kernel<false, true><<<grid, kFusedThreads + kTailThreads, kFusedSmem, stream>>>(map, P);
+    else           conv_stack_fused_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
     return (int)cudaGetLastError();
 }
 
 // One launch for n device-resident images.
 inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8_t* d_imgs, int64_t n, uint8_t* d_feats,
-                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1) {
+                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const TailArgs* tail = nullptr) {
     if (n <= 0) return 0;
     CUtensorMap map;
     int rc = fused_encode_map(d_imgs, n, &map);
     if (rc) return rc;
-    return launch_fused_map(fw, stream, map, n, d_feats, shifts, sm_count, dump_l0, dump_l1);
+    return launch_fused_map(fw, stream, map, n, d_feats, shifts, sm_count, dump_l0, dump_l1, nullptr, tail);
 }
 
 // Reads (and clears) the status word; non-zero = a pipeline wait timed out inside some launch.  The caller has

@@ -1,6 +1,13 @@
-// tail.cuh -- follow-on kernel: 4x4 spatial-bin pool -> linear -> softmax -> argmax -> CAM bbox.
+// tail.cuh -- follow-on stage: 4x4 spatial-bin pool -> linear -> softmax -> argmax -> CAM bbox.
 //
-// One CTA (256 threads) per image, reading the 64x16x16 u8 feature map (16 KiB) once from HBM/L2.
+// tail_image(): 64 threads (two warps) take one 64x16x16 u8 feature map that sits in SHARED memory (CHW, 16 KiB) to its
+// 44 bytes of predictions.  It has two callers:
+//   * conv_fused.cuh: two extra warps of the conv-stack kernel run it on the layer-2 staging buffer while the tensor
+//     core and the epilogue warps are already busy with the next image -- the features never leave the SM and, when the
+//     caller passes no feature pointer, HBM sees 44 B per image instead of 16 KiB out + 16 KiB back in;
+//   * classify_bbox_kernel below (features-in entry point, cnnacc_classify_batch): eight such groups per CTA.
+// Both produce bit-identical predictions because they are the same code on the same bytes.
+//
 // Reference (all /root/reference/software/realtime_detect.py):
 //   classify_vec :68-82   pooled[ch*16 + r*4 + c] = mean of the 4x4 bin of (feat/255); logits = W.pooled + b;
 //                         softmax; argmax
@@ -9,7 +16,8 @@
 // Numerics:
 //   * bin sums are exact integers; pooled = S / 4080 in one rounding (identical to Classifier.classify's
 //     mean-then-/255, pynq_inference.py:325-334; within 1 ulp of classify_vec's /255-then-mean);
-//   * logits: fp32, fixed summation tree (4 bins per thread, warp shuffle tree, 8 warp partials in order);
+//   * logits: fp32, fixed summation tree (4 bins per task, 4 tasks per thread in order, warp shuffle tree, two warp
+//     partials, bias last);
 //   * CAM: products and sums rounded separately (no FMA) in channel order 0..63, as numpy's reduction over
 //     the outer axis does, so the bbox integers match bit for bit given the same class;
 //   * percentile(70) of 256 values = index 178.5 -> hi - (hi-lo)*0.5 in fp32 (numpy _lerp with t = 0.5).
@@ -19,160 +27,292 @@
 namespace cnnacc {
 
 constexpr int kMaxClasses = 16;
+constexpr int kTailThreads = 64;                // threads that cooperate on one image
 
-__global__ void __launch_bounds__(256)
-classify_bbox_kernel(const uint8_t* __restrict__ feats, const float* __restrict__ fc_w,
-                     const float* __restrict__ fc_b, int n_cls,
-                     float* __restrict__ probs, int32_t* __restrict__ cls_out, int32_t* __restrict__ bbox_out,
-                     const int32_t* __restrict__ cls_in)
+struct TailArgs {
+    const float* fc_w;                          // [n_cls][1024] row-major
+    const float* fc_b;                          // [n_cls]
+    int n_cls;
+    int want_logits;                            // probs receives the raw logits instead of the softmax (CNNACC_FLAG_LOGITS)
+    float* probs;                               // [n][n_cls] or null
+    int32_t* cls_out;                           // [n] or null
+    int32_t* bbox_out;                          // [n][4] or null (null: the CAM stage is skipped)
+    const int32_t* cls_in;                      // [n] or null: bbox_vec's cls_idx argument (CNNACC_FLAG_CLS_GIVEN)
+};
+
+struct __align__(16) TailScratch {              // per 64-thread group
+    float sort[256];                            // one cross-warp exchange of the bitonic sort
+    float part[2][kMaxClasses];                 // per-warp logit partials
+    unsigned long long valid[2];                // per warp: bit ch = channel ch is not saturated (mean <= 250)
+    float red[2];
+    float thr;
+    int pad;
+    int box[2][4];
+};
+constexpr int kTailScratchBytes = 1280;
+static_assert(sizeof(TailScratch) <= kTailScratchBytes, "tail scratch");
+
+__device__ __forceinline__ void tail_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kTailThreads) : "memory"); }
+
+// u8 -> f32 through the 2^23 mantissa trick: one PRMT builds 0x4B0000bb, one FADD removes 2^23 (exact for 0..255)
+// instead of a quarter-rate I2F.
+template <int kByte>
+__device__ __forceinline__ float byte_to_float(uint32_t word) {
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + kByte)), 8388608.0f);
+}
+
+// Classifier rows the tail keeps in shared memory.  The rows do not depend on the image, but a 64-thread group cannot
+// hold its 96 weights per thread in registers, and from global memory every image pays L2 latency for them: next to
+// 217 KB of shared memory the SM's L1 is 28 KB and held only 69 % of the 24 KiB (ncu, profiles/r2_fusedtail_v1_*),
+// which made the logits 11 k of the tail's 21 k clk per image.  Rows that do not fit stay on the __ldg path.
+struct TailWeights {
+    const float* smem;                          // [rows][1024] in shared memory (may be null)
+    int rows;
+    float bias;                                 // fc_b[lane] for lane < n_cls, read once per kernel
+};
+
+// Copies min(n_cls, max_rows) classifier rows into shared memory; call with all 64 threads of the group, then tail_bar.
+__device__ __forceinline__ TailWeights tail_stage_weights(float* dst, int max_rows, const TailArgs& A, const int T) {
+    TailWeights W;
+    W.rows = min(A.n_cls, max_rows);
+    W.smem = dst;
+    for (int i = T; i < W.rows * 256; i += kTailThreads)
+        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(A.fc_w) + i);
+    W.bias = (T & 31) < A.n_cls ? __ldg(A.fc_b + (T & 31)) : 0.f;
+    return W;
+}
+
+// T = 0..63 within the group; bar_id = a named barrier reserved for these 64 threads; release() is called by every thread
+// after its last read of `stg` (the fused kernel hands the staging buffer back to the epilogue warps there).
+struct TailNoTrace { __device__ __forceinline__ void operator()(int) const {} };
+
+template <typename Release, typename Trace = TailNoTrace>
+__device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, TailScratch* sc, const int T, const int bar_id,
+                                           const TailArgs& A, const TailWeights& W, const size_t img, Release release,
+                                           Trace trace = Trace())
 {
-    __shared__ __align__(16) uint8_t s_feat[64 * 256];
-    __shared__ float s_part[8][kMaxClasses];
-    __shared__ float s_cam[256];
-    __shared__ __align__(16) float s_wc[1024];           // class weights of the chosen class, masked
-    __shared__ float s_red[8];
-    __shared__ int   s_valid[64];
-    __shared__ int   s_cls;
-    __shared__ float s_lohi[2];
-    __shared__ int   s_box[4];
+    trace(1);
+    const int lane = T & 31, w = T >> 5;
+    const unsigned full = 0xffffffffu;
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const size_t img = blockIdx.x;
-    const uint4* src = reinterpret_cast<const uint4*>(feats + img * 16384);
-
-    // thread t owns channel t/4, bin-row t%4: four 16-byte map rows = 64 contiguous bytes
-    int S[4] = {0, 0, 0, 0};
+    // ---- bin sums: task q = T + 64 i owns channel q/4, bin-row q%4 = four 16-byte map rows (64 contiguous bytes, read in a
+    // per-lane rotated order so that the eight lanes of a 128-bit wavefront hit eight different 16-byte bank groups) ----
+    int S[4][4];
+    unsigned long long vbits = 0;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        uint4 v = src[t * 4 + r];
-        reinterpret_cast<uint4*>(s_feat)[t * 4 + r] = v;
-        S[0] = __dp4a(v.x, 0x01010101u, (unsigned)S[0]);
-        S[1] = __dp4a(v.y, 0x01010101u, (unsigned)S[1]);
-        S[2] = __dp4a(v.z, 0x01010101u, (unsigned)S[2]);
-        S[3] = __dp4a(v.w, 0x01010101u, (unsigned)S[3]);
-    }
-    // channel mean <= 250  <=>  channel sum <= 64000 (bbox_vec: valid = ch_means <= 250)
-    int chsum = S[0] + S[1] + S[2] + S[3];
-    chsum += __shfl_xor_sync(0xffffffffu, chsum, 1);
-    chsum += __shfl_xor_sync(0xffffffffu, chsum, 2);
-    if ((t & 3) == 0) s_valid[t >> 2] = (chsum <= 250 * 256);
-
-    float pooled[4];
+    for (int i = 0; i < 4; i++) {
+        const uint4* p = reinterpret_cast<const uint4*>(stg + (T + 64 * i) * 64);
+        S[i][0] = S[i][1] = S[i][2] = S[i][3] = 0;
 #pragma unroll
-    for (int c = 0; c < 4; c++) pooled[c] = __fdiv_rn((float)S[c], 4080.0f);
-
-    // logits: W row-major [n_cls][1024]; this thread's bins are 4t .. 4t+3
-    for (int k = 0; k < n_cls; k++) {
-        float4 w = reinterpret_cast<const float4*>(fc_w + (size_t)k * 1024)[t];
-        float p = pooled[0] * w.x;
-        p = fmaf(pooled[1], w.y, p);
-        p = fmaf(pooled[2], w.z, p);
-        p = fmaf(pooled[3], w.w, p);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-        if (lane == 0) s_part[warp][k] = p;
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        float logit = -INFINITY;
-        if (lane < n_cls) {
-            float a = 0.f;
-#pragma unroll
-            for (int w8 = 0; w8 < 8; w8++) a += s_part[w8][lane];
-            logit = a + fc_b[lane];
+        for (int r = 0; r < 4; r++) {
+            const uint4 v = p[(r + (T >> 1)) & 3];
+            S[i][0] = __dp4a(v.x, 0x01010101u, (unsigned)S[i][0]);
+            S[i][1] = __dp4a(v.y, 0x01010101u, (unsigned)S[i][1]);
+            S[i][2] = __dp4a(v.z, 0x01010101u, (unsigned)S[i][2]);
+            S[i][3] = __dp4a(v.w, 0x01010101u, (unsigned)S[i][3]);
         }
-        float mx = logit;
-        int arg = lane < n_cls ? lane : 0x7fffffff;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            float om = __shfl_xor_sync(0xffffffffu, mx, off);
-            int   oa = __shfl_xor_sync(0xffffffffu, arg, off);
-            if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // first maximum, like np.argmax
-        }
-        float e = lane < n_cls ? expf(logit - mx) : 0.f;
-        float sum = e;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (probs && lane < n_cls) probs[img * n_cls + lane] = __fdiv_rn(e, sum);
-        if (lane == 0) {
-            // bbox_vec takes the class as an argument (realtime_detect.py:85); cls_in carries it when given
-            s_cls = cls_in ? min(max(cls_in[img], 0), n_cls - 1) : arg;
-            if (cls_out && !cls_in) cls_out[img] = arg;
-            s_box[0] = 16; s_box[1] = 16; s_box[2] = -1; s_box[3] = -1;   // min col, min row, max col, max row
-        }
+        // channel mean <= 250  <=>  channel sum <= 64000 (bbox_vec: valid = ch_means <= 250)
+        int cs = S[i][0] + S[i][1] + S[i][2] + S[i][3];
+        cs += __shfl_xor_sync(full, cs, 1);
+        cs += __shfl_xor_sync(full, cs, 2);
+        // lanes 4q..4q+3 of warp w hold channel 16 i + 8 w + q: squeeze ballot bits 0,4,..,28 into one byte
+        uint32_t b = __ballot_sync(full, cs <= 250 * 256) & 0x11111111u;
+        b = (b | (b >> 3)) & 0x03030303u;
+        b = (b | (b >> 6)) & 0x000F000Fu;
+        b = (b | (b >> 12)) & 0xFFu;
+        vbits |= (unsigned long long)b << (16 * i + 8 * w);
     }
-    __syncthreads();
-    if (!bbox_out) return;
+    if (lane == 0) sc->valid[w] = vbits;                  // each warp knows half of the channels
+    trace(2);
 
-    // CAM: thread t owns pixel t = (py, px); class weights indexed [ch*16 + (py/4)*4 + px/4].  The masked class weights
-    // (0 for saturated channels) are staged once per image; u8 -> f32 goes through the 2^23 mantissa trick (one LOP3 +
-    // one FADD, exact for 0..255) instead of the quarter-rate I2F.
-    reinterpret_cast<float4*>(s_wc)[t] = s_valid[t >> 2] ? __ldg(reinterpret_cast<const float4*>(fc_w + (size_t)s_cls * 1024) + t)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int py = t >> 4, px = t & 15;
-    const float* wc = s_wc + (py >> 2) * 4 + (px >> 2);
-    float cam = 0.f;
+    // ---- logits: W row-major [n_cls][1024]; task q covers bins 4q .. 4q+3 ----
+    float pooled[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) pooled[i][c] = __fdiv_rn((float)S[i][c], 4080.0f);
+#pragma unroll 2
+    for (int k = 0; k < A.n_cls; k++) {
+        const bool in_smem = k < W.rows;                  // uniform
+        const float4* wr = reinterpret_cast<const float4*>((in_smem ? W.smem : A.fc_w) + (size_t)k * 1024) + T;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float4 wv;
+            if (in_smem) wv = wr[64 * i]; else wv = __ldg(wr + 64 * i);
+            float p = pooled[i][0] * wv.x;
+            p = fmaf(pooled[i][1], wv.y, p);
+            p = fmaf(pooled[i][2], wv.z, p);
+            p = fmaf(pooled[i][3], wv.w, p);
+            acc = i ? acc + p : p;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(full, acc, off);
+        if (lane == 0) sc->part[w][k] = acc;
+    }
+    trace(3);
+    tail_bar(bar_id);                                     // #1: partials and the valid mask are visible
+
+    // ---- softmax / argmax: every warp computes it (no second barrier), warp 0 writes ----
+    float logit = -INFINITY;
+    if (lane < A.n_cls) logit = (sc->part[0][lane] + sc->part[1][lane]) + W.bias;
+    float mx = logit;
+    int arg = lane < A.n_cls ? lane : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float om = __shfl_xor_sync(full, mx, off);
+        const int   oa = __shfl_xor_sync(full, arg, off);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // first maximum, like np.argmax
+    }
+    const float e = lane < A.n_cls ? expf(logit - mx) : 0.f;
+    float sum = e;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(full, sum, off);
+    if (w == 0) {
+        if (A.probs && lane < A.n_cls) A.probs[img * A.n_cls + lane] = A.want_logits ? logit : __fdiv_rn(e, sum);
+        if (lane == 0 && A.cls_out && !A.cls_in) A.cls_out[img] = arg;
+    }
+    if (!A.bbox_out) {                                    // uniform: a kernel argument
+        release();
+        tail_bar(bar_id);                                 // everyone has read sc->part before the next image overwrites it
+        return;
+    }
+    trace(4);
+    // bbox_vec takes the class as an argument (realtime_detect.py:85); cls_in carries it when given
+    const int cls = A.cls_in ? min(max(A.cls_in[img], 0), A.n_cls - 1) : arg;
+
+    // ---- CAM: thread T owns pixels 4T .. 4T+3 = row T/4, columns 4(T%4) .. +3, all in bin (T/16, T%4), so one class weight
+    // and one 32-bit feature word per channel serve four pixels.  Saturated channels contribute w = 0. ----
+    const unsigned long long valid = sc->valid[0] | sc->valid[1];
+    const bool cam_smem = cls < W.rows;                   // uniform: every thread has the same class
+    const float* wc = (cam_smem ? W.smem : A.fc_w) + (size_t)cls * 1024 + (T >> 4) * 4 + (T & 3);
+    const uint32_t* fwp = reinterpret_cast<const uint32_t*>(stg) + T;
+    float cam[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 16
     for (int ch = 0; ch < 64; ch++) {
-        const float f = __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)s_feat[ch * 256 + t]), 8388608.0f);
-        cam = __fadd_rn(cam, __fmul_rn(wc[ch * 16], f));
+        float wv;
+        if (cam_smem) wv = wc[ch * 16]; else wv = __ldg(wc + ch * 16);
+        wv = ((valid >> ch) & 1ull) ? wv : 0.f;
+        const uint32_t word = fwp[ch * 64];
+        cam[0] = __fadd_rn(cam[0], __fmul_rn(wv, byte_to_float<0>(word)));
+        cam[1] = __fadd_rn(cam[1], __fmul_rn(wv, byte_to_float<1>(word)));
+        cam[2] = __fadd_rn(cam[2], __fmul_rn(wv, byte_to_float<2>(word)));
+        cam[3] = __fadd_rn(cam[3], __fmul_rn(wv, byte_to_float<3>(word)));
     }
-    cam = fmaxf(cam, 0.f);
-
-    float m = cam;
+    release();                                            // last read of the feature map
+    trace(5);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (lane == 0) s_red[warp] = m;
-    __syncthreads();
-    m = s_red[0];
-#pragma unroll
-    for (int w8 = 1; w8 < 8; w8++) m = fmaxf(m, s_red[w8]);
-    if (m > 0.f) cam = __fdiv_rn(cam, m);
+    for (int b = 0; b < 4; b++) cam[b] = fmaxf(cam[b], 0.f);
 
-    // 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort, one value per thread:
-    // strides < 32 exchange by shuffle, strides >= 32 through shared memory (36 compare-exchange stages instead of
-    // the 256-step rank-by-counting loop this replaced).
-    float v = cam;
+    float m = fmaxf(fmaxf(cam[0], cam[1]), fmaxf(cam[2], cam[3]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, off));
+    if (lane == 0) sc->red[w] = m;
+    tail_bar(bar_id);                                     // #2
+    m = fmaxf(sc->red[0], sc->red[1]);
+    if (m > 0.f) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) cam[b] = __fdiv_rn(cam[b], m);
+    }
+
+    // ---- 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort of element e = 4T + b:
+    // strides 1, 2 stay inside the thread, 4..64 are warp shuffles (lane ^ stride/4), 128 is one exchange through
+    // shared memory. ----
+    trace(6);
+    float v[4] = {cam[0], cam[1], cam[2], cam[3]};
 #pragma unroll
     for (int k = 2; k <= 256; k <<= 1) {
+        const bool up = (k == 2) ? true : (k == 256 ? true : ((T & (k >> 2)) == 0));   // k == 2: decided per pair below
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            float o;
-            if (j >= 32) {
-                __syncthreads();                         // previous readers of s_cam are done
-                s_cam[t] = v;
-                __syncthreads();
-                o = s_cam[t ^ j];
+            if (j == 128) {
+                reinterpret_cast<float4*>(sc->sort)[T] = make_float4(v[0], v[1], v[2], v[3]);
+                tail_bar(bar_id);                         // #3
+                const float4 o = reinterpret_cast<const float4*>(sc->sort)[T ^ 32];
+                const bool lower = (T & 32) == 0;         // k = 256: every block ascends
+                v[0] = lower ? fminf(v[0], o.x) : fmaxf(v[0], o.x);
+                v[1] = lower ? fminf(v[1], o.y) : fmaxf(v[1], o.y);
+                v[2] = lower ? fminf(v[2], o.z) : fmaxf(v[2], o.z);
+                v[3] = lower ? fminf(v[3], o.w) : fmaxf(v[3], o.w);
+            } else if (j >= 4) {
+                const bool keep_min = (((T & (j >> 2)) == 0) == up);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const float o = __shfl_xor_sync(full, v[b], j >> 2);
+                    v[b] = keep_min ? fminf(v[b], o) : fmaxf(v[b], o);
+                }
             } else {
-                o = __shfl_xor_sync(0xffffffffu, v, j);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a & j) continue;
+                    const bool asc = (k == 2) ? ((a & 2) == 0) : up;
+                    const float lo = fminf(v[a], v[a | j]), hi = fmaxf(v[a], v[a | j]);
+                    v[a] = asc ? lo : hi;
+                    v[a | j] = asc ? hi : lo;
+                }
             }
-            const bool up = ((t & k) == 0);              // ascending block
-            const bool lower = ((t & j) == 0);           // this thread keeps the smaller one in an ascending block
-            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
         }
     }
-    if (t == 178) s_lohi[0] = v;
-    if (t == 179) s_lohi[1] = v;
-    __syncthreads();
-    const float lo = s_lohi[0], hi = s_lohi[1];
-    float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
-    thr = (0.25f > thr) ? 0.25f : thr;                      // python max(p, 0.25)
-    if (cam > thr) {
-        atomicMin(&s_box[0], px); atomicMin(&s_box[1], py);
-        atomicMax(&s_box[2], px); atomicMax(&s_box[3], py);
+    trace(7);
+    if (T == 44) {                                        // elements 178, 179 = thread 44, b = 2, 3
+        const float lo = v[2], hi = v[3];
+        float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
+        sc->thr = (0.25f > thr) ? 0.25f : thr;            // python max(p, 0.25)
     }
+    tail_bar(bar_id);                                     // #4
+    const float thr = sc->thr;
+    const int x0 = 4 * (T & 3), y = T >> 2;
+    int xmin = 16, xmax = -1;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (cam[b] > thr) { xmin = min(xmin, x0 + b); xmax = max(xmax, x0 + b); }
+    int ymin = xmax >= 0 ? y : 16, ymax = xmax >= 0 ? y : -1;
+    xmin = __reduce_min_sync(full, xmin); ymin = __reduce_min_sync(full, ymin);
+    xmax = __reduce_max_sync(full, xmax); ymax = __reduce_max_sync(full, ymax);
+    if (lane == 0) { sc->box[w][0] = xmin; sc->box[w][1] = ymin; sc->box[w][2] = xmax; sc->box[w][3] = ymax; }
+    tail_bar(bar_id);                                     // #5
+    if (T == 0) {
+        xmin = min(sc->box[0][0], sc->box[1][0]); ymin = min(sc->box[0][1], sc->box[1][1]);
+        xmax = max(sc->box[0][2], sc->box[1][2]); ymax = max(sc->box[0][3], sc->box[1][3]);
+        int4 bx;
+        if (xmax >= 0) bx = make_int4(xmin * 8, ymin * 8, min(127, (xmax + 1) * 8), min(127, (ymax + 1) * 8));
+        else bx = make_int4(0, 0, 127, 127);
+        reinterpret_cast<int4*>(A.bbox_out)[img] = bx;
+    }
+    trace(8);
+}
+
+// Features-in entry point (cnnacc_classify_batch): persistent CTAs of eight 64-thread groups; a group copies its image's
+// 16 KiB map into its own shared-memory slot (16 independent 128-bit loads per thread) and runs tail_image on it.
+constexpr int kTailGroups = 8;
+constexpr int kTailSmemW = kMaxClasses * 4096;          // every classifier row, shared by the eight groups
+constexpr int kTailSmem = kTailGroups * (16384 + kTailScratchBytes) + kTailSmemW;
+
+__global__ void __launch_bounds__(kTailGroups * kTailThreads, 1)
+classify_bbox_kernel(const uint8_t* __restrict__ feats, long long n, const TailArgs A)
+{
+    extern __shared__ __align__(16) uint8_t tail_smem[];
+    const int g = threadIdx.x >> 6, T = threadIdx.x & 63;
+    uint8_t* stg = tail_smem + g * 16384;
+    TailScratch* sc = reinterpret_cast<TailScratch*>(tail_smem + kTailGroups * 16384 + g * kTailScratchBytes);
+    float* wsm = reinterpret_cast<float*>(tail_smem + kTailGroups * (16384 + kTailScratchBytes));
+    // group g stages rows g, g+8 (every group ends with the same view after the CTA barrier)
+    for (int i = threadIdx.x; i < A.n_cls * 256; i += kTailGroups * kTailThreads)
+        reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(A.fc_w) + i);
+    TailWeights W;
+    W.smem = wsm; W.rows = A.n_cls;
+    W.bias = (T & 31) < A.n_cls ? __ldg(A.fc_b + (T & 31)) : 0.f;
     __syncthreads();
-    if (t == 0) {
-        int4 b;
-        if (s_box[2] >= 0) {
-            b.x = s_box[0] * 8; b.y = s_box[1] * 8;
-            b.z = min(127, (s_box[2] + 1) * 8); b.w = min(127, (s_box[3] + 1) * 8);
-        } else {
-            b = make_int4(0, 0, 127, 127);
-        }
-        reinterpret_cast<int4*>(bbox_out)[img] = b;
+    for (long long img = (long long)blockIdx.x * kTailGroups + g; img < n; img += (long long)gridDim.x * kTailGroups) {
+        const uint4* src = reinterpret_cast<const uint4*>(feats + (size_t)img * 16384);
+        uint4 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) v[r] = __ldcs(src + T + 64 * r);       // read once: streaming
+#pragma unroll
+        for (int r = 0; r < 16; r++) reinterpret_cast<uint4*>(stg)[T + 64 * r] = v[r];
+        tail_bar(1 + g);
+        tail_image(stg, sc, T, 1 + g, A, W, (size_t)img, [] {});
+        tail_bar(1 + g);                                  // every thread is done with stg before it is overwritten
     }
 }
 

@@ -47,6 +47,9 @@ extern "C" {
 #define CNNACC_FLAG_CLS_GIVEN     0x8u  /* classify_batch: cls[] is an INPUT (bbox_vec's cls_idx argument), not written */
 #define CNNACC_FLAG_BBOX_UPSAMPLED 0x10u /* classify_batch / infer_batch: bbox = Classifier.get_cam_bbox (pynq_inference.py:349-408:
                                             u8 CAM -> PIL bilinear 16->128 -> percentile / 0.2 floor -> pad 3) instead of bbox_vec */
+#define CNNACC_FLAG_LOGITS        0x20u /* classify_batch / infer_batch / detect_frames: probs[] receives the raw fp32 logits
+                                            W.pooled + b (realtime_detect.py:79) instead of their softmax -- the quantity the
+                                            1e-5-relative parity bar is stated on */
 
 typedef struct cnnacc_handle cnnacc_handle;
 
@@ -71,6 +74,13 @@ int cnnacc_load_weights(cnnacc_handle *h, const uint8_t *weights_bin, size_t n);
  * masks with 0x1F; here values outside 0..31 are rejected with -2 (C >> by >=32 is undefined). */
 int cnnacc_set_shifts(cnnacc_handle *h, int s0, int s1, int s2);
 int cnnacc_get_shifts(const cnnacc_handle *h, int *s3);
+/* Accumulator width of the conv stack.  32 (default) = arm_cnn.c:31,106 (int32, never wraps: the parity target).
+ * 24 = the PL accumulator (rtl/core/accumulator.v:15 `reg signed [23:0]`) and the trainer's bit-accurate model
+ * (training/train_cnn.py:101-116 fpga_conv_layer: ((out + 2^23) mod 2^24) - 2^23 before the shift): every finished sum is
+ * wrapped to 24-bit two's complement BEFORE the 2x2 pool.  Only layer 2 can reach 2^23 (32*9*255*128 = 9.4 M); the shipped
+ * weights never do.  The RTL's spatial quirks (bottom-right window anchor, no left/right padding) are NOT modelled. */
+int cnnacc_set_accumulator_bits(cnnacc_handle *h, int bits);
+int cnnacc_get_accumulator_bits(const cnnacc_handle *h);
 /* Host-only view of the one-off weight permutation (parse_kernels, arm_cnn.c:43-59, hoisted out of the
  * per-image path): weights.bin -> the fused kernel's operand images.  No GPU needed; tests/ re-derive the conv
  * from these buffers to pin the packed layouts.  w0: 96 dp4a words
@@ -153,11 +163,18 @@ int cnnacc_detect_frames(cnnacc_handle *h, const uint8_t *frames, int64_t n, int
 /* ---- host memory the DMA engines can stream from (pynq.allocate, realtime_detect.py:293,301) */
 int cnnacc_alloc_host(size_t bytes, void **out);
 int cnnacc_free_host(void *p);
+/* Page-lock memory the caller already owns (e.g. a shared-memory mapping that several per-GPU processes write their slice of
+ * the prediction array into: SURVEY.md 8e "per-GPU D2H into one pinned host array"). */
+int cnnacc_register_host(void *p, size_t bytes);
+int cnnacc_unregister_host(void *p);
 
 /* ---- timing on the handle's stream (CUDA events; bench.py) ---------------------------------- */
 int cnnacc_timer_start(cnnacc_handle *h);
 int cnnacc_timer_stop(cnnacc_handle *h, float *ms);   /* synchronises the stream */
 int cnnacc_synchronize(cnnacc_handle *h);
+/* Dense int8 tensor-core ceiling of this GPU, measured now: back-to-back tcgen05.mma kind::i8 M=128 N=256 K=32 on every SM
+ * for about target_ms milliseconds (csrc/int8_peak_probe.cuh).  *tops = 10^12 integer ops per second (2 per MAC). */
+int cnnacc_probe_int8_peak(cnnacc_handle *h, double target_ms, double *tops, double *ms);
 
 /* ---- drop-in for the reference symbol ------------------------------------------------------
  * Same name and signature as arm_cnn.c:159-162, so ARMEngine's ctypes call

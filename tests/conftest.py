@@ -41,3 +41,8 @@ def cam_golden():
 @pytest.fixture(scope="session")
 def prep_golden():
     return np.load(os.path.join(GOLDEN, "prep_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def acc24_golden():
+    return np.load(os.path.join(GOLDEN, "acc24_cases.npz"))

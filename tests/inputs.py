@@ -47,11 +47,26 @@ def make_images(kind, n, H=128, W=128):
         return smooth_images(arg, n, H, W)
     if tag == "const":
         return np.full((n, H, W), arg, dtype=np.uint8)
+    if tag == "bright":                         # 160..255: keeps the early layers near saturation (24-bit wrap cases)
+        return np.random.default_rng(arg).integers(160, 256, (n, H, W), dtype=np.uint8)
     raise ValueError(kind)
 
 
+def pack_weights(kernels):
+    """[k0 (16,1,3,3), k1 (32,16,3,3), k2 (64,32,3,3)] int -> weights.bin bytes, file order [layer][ob][ic][c16][tap9]
+    (the inverse of parse_kernels, arm_cnn.c:43-59; the writer is train_cnn.py:174-195)."""
+    out = []
+    for k in kernels:
+        oc, ic = k.shape[:2]
+        raw = np.asarray(k, dtype=np.int8).reshape(oc // 16, 16, ic, 3, 3).transpose(0, 2, 1, 3, 4)
+        out.append(np.ascontiguousarray(raw).reshape(-1).view(np.uint8))
+    w = np.concatenate(out)
+    assert w.size == NUM_WEIGHT_BYTES
+    return w
+
+
 def make_weights(kind, shipped=None):
-    """kind: 'shipped' | 'identity' | ('rng', seed) | ('const', byte) | ('sparse', seed)."""
+    """kind: 'shipped' | 'identity' | ('rng', seed) | ('const', byte) | ('sparse', seed) | ('acc24', seed) | 'acc24_extreme'."""
     if kind == "shipped":
         assert shipped is not None and shipped.size == NUM_WEIGHT_BYTES
         return np.array(shipped, dtype=np.uint8)
@@ -59,7 +74,17 @@ def make_weights(kind, shipped=None):
         w = np.zeros(NUM_WEIGHT_BYTES, dtype=np.uint8)
         w[4] = 1
         return w
+    if kind == "acc24_extreme":                 # every layer-2 sum of an interior pixel is +-288*127*255 = +-9.33 M: beyond 2^23
+        k2 = np.where((np.arange(64) % 2 == 0)[:, None, None, None], 127, -127) * np.ones((64, 32, 3, 3), dtype=np.int64)
+        return pack_weights([np.full((16, 1, 3, 3), 127), np.full((32, 16, 3, 3), 127), k2])
     tag, arg = kind
+    if tag == "acc24":                          # large same-sign layer-2 kernels on near-saturated inputs: sums straddle 2^23
+        rng = np.random.default_rng(arg)
+        k0 = rng.integers(64, 128, (16, 1, 3, 3))
+        k1 = rng.integers(rng.integers(70, 125, (32, 1, 1, 1)), 128, (32, 16, 3, 3))
+        sign = np.where(np.arange(64) % 3 == 2, -1, 1)[:, None, None, None]
+        k2 = sign * rng.integers(rng.integers(100, 127, (64, 1, 1, 1)), 128, (64, 32, 3, 3))
+        return pack_weights([k0, k1, k2])
     if tag == "rng":                            # full range: bytes 0..255 == s8 -128..127
         return np.random.default_rng(arg).integers(0, 256, NUM_WEIGHT_BYTES, dtype=np.uint8)
     if tag == "const":
@@ -95,6 +120,18 @@ CONV_CASES = [
     dict(name="min_neg_weights", weights=("const", 0x80), images=("rng", 8), n=1, shifts=(0, 0, 0)),
     dict(name="sparse_weights", weights=("sparse", 9), images=("rng", 10), n=3, shifts=(5, 7, 8), tail=True),
     dict(name="mixed_shifts", weights=("rng", 12), images=("smooth", 13), n=3, shifts=(3, 13, 9)),
+]
+
+# 24-bit wrapping accumulator (cnnacc_set_accumulator_bits(24)): outputs produced by the reference's own bit-accurate model,
+# training/train_cnn.py:101-116 fpga_conv_layer, through tests/golden/make_acc24_golden.py -> acc24_cases.npz.  Weights stay
+# within +-127 (that function clamps them).  The *_wrap cases are built so that layer 2 really leaves the 24-bit range.
+ACC24_CASES = [
+    dict(name="acc24_extreme", weights="acc24_extreme", images=("const", 255), n=1, shifts=(0, 0, 15), wraps=True),
+    dict(name="acc24_wrap_a", weights=("acc24", 31), images=("bright", 32), n=3, shifts=(0, 14, 15), wraps=True),
+    dict(name="acc24_wrap_b", weights=("acc24", 33), images=("bright", 34), n=3, shifts=(0, 13, 16), wraps=True),
+    dict(name="acc24_wrap_smooth", weights=("acc24", 35), images=("smooth", 36), n=2, shifts=(0, 14, 15), wraps=True),
+    dict(name="acc24_shipped_nowrap", weights="shipped", images=("rng", 1), n=4, shifts=(7, 10, 11), wraps=False),
+    dict(name="acc24_sparse_nowrap", weights=("sparse", 9), images=("rng", 10), n=2, shifts=(5, 7, 8), wraps=False, clamp127=True),
 ]
 
 # generic H x W cases (oracle = arm_benchmark.arm_conv_layer; arm_cnn.c is 128x128 only)

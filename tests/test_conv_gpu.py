@@ -259,3 +259,75 @@ def test_two_host_threads_two_handles(fc, port, shipped_weights):
     for a in accs:
         a.close()
     assert not bad
+
+
+@pytest.mark.parametrize("direct", [False, True], ids=["fused", "direct"])
+@pytest.mark.parametrize("case", inputs.ACC24_CASES, ids=lambda c: c["name"])
+def test_acc24_mode_vs_trainer_fixtures(case, direct, fc, shipped_weights, acc24_golden):
+    """cnnacc_set_accumulator_bits(24): byte-equal to the reference's own bit-accurate model (train_cnn.fpga_conv_layer,
+    fixtures from tests/golden/make_acc24_golden.py) on wrapping and non-wrapping cases; the default mode is untouched."""
+    wt = inputs.make_weights(case["weights"], shipped_weights)
+    if case.get("clamp127"):
+        wt = inputs.pack_weights([np.maximum(k, -127) for k in oracle.np_oracle.unpack_weights(wt)])
+    imgs = inputs.make_images(case["images"], case["n"])
+    a = fc.CNNAccelerator()
+    a.load_weights(wt)
+    a.set_shifts(*case["shifts"])
+    assert a.get_accumulator_bits() == 32
+    plain = a.run_batch(imgs, direct=direct).reshape(case["n"], 64, 256)
+    assert np.array_equal(plain, oracle.port_infer_batch(oracle.load_port(), imgs, wt, case["shifts"]))
+    a.set_accumulator_bits(24)
+    assert a.get_accumulator_bits() == 24
+    got = a.run_batch(imgs, direct=direct).reshape(case["n"], 64, 256)
+    assert np.array_equal(got, acc24_golden[case["name"]]), np.argwhere(got != acc24_golden[case["name"]])[:5]
+    assert np.array_equal(got, plain) != case["wraps"]
+    with pytest.raises(ValueError):
+        a.set_accumulator_bits(16)
+    a.set_accumulator_bits(32)
+    assert np.array_equal(a.run_batch(imgs, direct=direct).reshape(case["n"], 64, 256), plain)
+    a.close()
+
+
+def test_acc24_random_vs_oracle_incl_windows(fc):
+    """More wrapping inputs than the fixtures hold, against the pinned numpy restatement, plus a 256x128 image through the
+    window mode (the wrap sits in the shared layer-2 epilogue)."""
+    a = fc.CNNAccelerator()
+    a.set_accumulator_bits(24)
+    for seed in (71, 72):
+        wt = inputs.make_weights(("acc24", seed))
+        kern = oracle.np_oracle.unpack_weights(wt)
+        a.load_weights(wt)
+        a.set_shifts(0, 14, 15)
+        imgs = inputs.make_images(("bright", seed + 10), 5)
+        got = a.run_batch(imgs).reshape(5, 64, 256)
+        for i in range(5):
+            assert np.array_equal(got[i], oracle.np_oracle.infer(imgs[i], kern, (0, 14, 15), acc_bits=24)), (seed, i)
+        big = inputs.make_images(("bright", seed + 20), 1, 256, 128)
+        want = oracle.np_oracle.infer(big[0], kern, (0, 14, 15), H=256, W=128, acc_bits=24)
+        assert np.array_equal(a.run_batch(big).reshape(64, -1), want)
+        assert np.array_equal(a.run_batch(big, direct=True).reshape(64, -1), want)
+    a.close()
+
+
+def test_torch_call_is_ordered_on_the_current_stream(fc, port, shipped_weights):
+    """Device-pointer calls run on torch's current stream unless use_stream() chose one: producer -> run_batch -> .cpu()
+    needs no explicit synchronisation, on the default stream and on a side stream."""
+    import torch
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    base = inputs.make_images(("rng", 90), 2048)
+    want = oracle.port_infer_batch(port, base[:64], shipped_weights, (7, 10, 11)).reshape(64, 64, 16, 16)
+    for stream in (None, torch.cuda.Stream()):
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            for rep in range(3):
+                t = torch.from_numpy(base).cuda(non_blocking=True)
+                t = (t ^ 0xFF) ^ 0xFF                     # a torch kernel produces the input on the current stream
+                got = a.run_batch(t).cpu()                # no use_stream, no synchronize
+                assert np.array_equal(got.numpy()[:64], want)
+                cls_f = a.run_batch(t[:64].clone())
+                assert np.array_equal(cls_f.cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        a.run_batch(torch.zeros((2, 128, 128), dtype=torch.uint8, device="cuda"), out=torch.zeros(5, dtype=torch.uint8, device="cuda"))
+    a.close()

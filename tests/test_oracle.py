@@ -206,3 +206,25 @@ def test_area_table_properties():
         assert np.allclose(w, 1.0, atol=1e-6)                     # each output pixel's weights sum to 1
         src = [s for _, s, _ in tab]
         assert src[0] == 0 and src[-1] == S - 1 and all(b - a in (0, 1) for a, b in zip(src, src[1:]))
+
+
+@pytest.mark.parametrize("case", inputs.ACC24_CASES, ids=lambda c: c["name"])
+def test_acc24_restatement_matches_trainer_fixtures(case, shipped_weights, acc24_golden):
+    """np_oracle.conv_layer(acc_bits=24) vs outputs of the reference's own fpga_conv_layer (train_cnn.py:101-116)."""
+    wt = inputs.make_weights(case["weights"], shipped_weights)
+    kern = np_oracle.unpack_weights(wt)
+    if case.get("clamp127"):
+        kern = [np.maximum(k, -127) for k in kern]
+    imgs = inputs.make_images(case["images"], case["n"])
+    for i in range(case["n"]):
+        got = np_oracle.infer(imgs[i], kern, case["shifts"], acc_bits=24)
+        assert np.array_equal(got, acc24_golden[case["name"]][i]), (case["name"], i)
+        same = np.array_equal(got, np_oracle.infer(imgs[i], kern, case["shifts"]))
+        assert same != case["wraps"]             # the wrap cases really leave the 24-bit range; the others never do
+
+
+def test_acc24_scalar_kats():
+    """accumulator_tb.v:28-61 (500 overwrite + 300 add = 800) stays 800 in 24 bits; 2^23 wraps to -2^23."""
+    m = 1 << 23
+    wrap = lambda v: ((v + m) % (2 * m)) - m
+    assert wrap(500 + 300) == 800 and wrap(m) == -m and wrap(-m - 1) == m - 1 and wrap(288 * 127 * 255) == 288 * 127 * 255 - 2 * m

@@ -1,8 +1,10 @@
 """Classifier / CAM tail on the GPU vs the reference's classify_vec / bbox_vec (numpy oracle + fixtures).
 
-Tolerance (north_star): logits within 1e-5 relative -- measured here on the softmax probabilities, which
-is the only thing the reference returns, as |p_gpu - p_ref| <= 1e-5 -- and identical argmax.  Bounding boxes
-are integer outputs and must match exactly.
+Tolerance (north_star / BASELINE.md section 2): fp32 logits within 1e-5 relative, measured against max|logit| of the
+image -- |logit_gpu - logit_ref| <= 1e-5 * max_k |logit_ref[k]| (LOGIT_RTOL; test_logits_within_stated_tolerance) -- and
+identical argmax except where the reference's own top-2 logits are closer than that band.  The softmax probabilities
+(the only thing the reference returns) are also held to |p_gpu - p_ref| <= 1e-5.  Bounding boxes are integer outputs
+and must match exactly.
 """
 import numpy as np
 import pytest
@@ -209,4 +211,107 @@ def test_pool_features_and_dump_round_trip(tmp_path, acc, shipped_weights):
     f = fc.dump_features(a, imgs, labels=[0, 1, 2, 3, 4, -1], names=[f"im{i}" for i in range(6)], output=str(out), shifts=(7, 10, 11))
     f2, labels, names, shifts = fc.load_features(str(out))
     assert np.array_equal(f, f2) and list(labels) == [0, 1, 2, 3, 4, -1] and names[5] == "im5" and shifts == (7, 10, 11)
+    a.close()
+
+
+# ---- the stated classifier bar: logits, 1e-5 relative to max|logit| ------------------------------------------------
+LOGIT_RTOL = 1e-5
+
+
+def _check_logits(feats, w, b, logits_gpu, cls_gpu):
+    """Returns the worst |dlogit| / max|logit| seen; asserts the bar and the argmax rule per image."""
+    worst = 0.0
+    for i in range(len(feats)):
+        c, _, ref, pooled = np_oracle.classify_vec(feats[i], w, b)
+        ref64 = pooled.astype(np.float64) @ w.astype(np.float64).T + b           # what both fp32 results approximate
+        scale = np.abs(ref).max()
+        err = np.abs(logits_gpu[i] - ref).max()
+        assert err <= LOGIT_RTOL * scale, f"image {i}: |dlogit| {err:.3e} > 1e-5 * max|logit| {scale:.3e}"
+        assert np.abs(logits_gpu[i] - ref64).max() <= LOGIT_RTOL * scale
+        worst = max(worst, err / scale)
+        if c != cls_gpu[i]:
+            top2 = np.sort(ref)[-2:]
+            assert top2[1] - top2[0] <= LOGIT_RTOL * scale, f"argmax differs on image {i} outside the tolerance band"
+    return worst
+
+
+def test_logits_within_stated_tolerance(acc, conv_golden):
+    w, b = inputs.make_fc()
+    worst = 0.0
+    for case in inputs.CONV_CASES:
+        if not case.get("tail"):
+            continue
+        feats = conv_golden[case["name"]]
+        cls, logits, _ = acc.classify_batch(feats, logits=True)
+        cls2, probs, _ = acc.classify_batch(feats)
+        assert np.array_equal(cls, cls2)
+        e = np.exp(logits - logits.max(axis=1, keepdims=True))
+        assert np.abs(e / e.sum(axis=1, keepdims=True) - probs).max() <= 2e-7      # probs are the softmax of these logits
+        worst = max(worst, _check_logits(feats, w, b, logits, cls))
+    for seed in (0, 1, 2):                                                        # the 900 random maps of the probs test
+        import fpga_cnn_b200 as fc
+        rng = np.random.default_rng(seed)
+        feats = _random_features(rng, 300)
+        w2, b2 = inputs.make_fc(seed=50 + seed)
+        a = fc.CNNAccelerator()
+        a.load_classifier(w2, b2)
+        cls, logits, _ = a.classify_batch(feats, logits=True)
+        worst = max(worst, _check_logits(feats, w2, b2, logits, cls))
+        a.close()
+    print(f"worst |dlogit| / max|logit| = {worst:.3e} (bar {LOGIT_RTOL:g})")
+    assert worst <= LOGIT_RTOL
+
+
+# ---- the tail inside the conv-stack kernel (infer_batch) ------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 147, 148, 149, 296, 297, 1000, 5000])
+def test_fused_tail_equals_features_path(n, shipped_weights):
+    """infer_batch = conv stack with the tail warps on the staged feature map (predictions only, no feature store) must
+    give exactly what run_batch -> classify_batch gives, at batch sizes around the SM count, through the latency path
+    (n <= 64), the host staging ring and device pointers."""
+    import torch
+    import fpga_cnn_b200 as fc
+    w, b = inputs.make_fc(seed=7)
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    a.load_classifier(w, b)
+    imgs = inputs.make_images(("rng", 2000 + n), n) if n % 2 else inputs.make_images(("smooth", 2000 + n), n)
+    feats = a.run_batch(imgs).reshape(n, 64, 256)
+    cls0, probs0, box0 = a.classify_batch(feats)
+    cls1, probs1, box1 = a.infer_batch(imgs)                                       # host pointers
+    assert np.array_equal(cls0, cls1) and np.array_equal(probs0, probs1) and np.array_equal(box0, box1)
+    t = torch.from_numpy(imgs).cuda()
+    cls2, probs2, box2 = a.infer_batch(t)                                          # device pointers, one fused launch
+    assert np.array_equal(cls0, cls2.cpu().numpy()) and np.array_equal(probs0, probs2.cpu().numpy()) and np.array_equal(box0, box2.cpu().numpy())
+    cls3, logit3, box3 = a.infer_batch(t, logits=True)
+    cls4, logit4, _ = a.classify_batch(feats, logits=True)
+    assert np.array_equal(logit3.cpu().numpy(), logit4) and np.array_equal(cls3.cpu().numpy(), cls4) and np.array_equal(box3.cpu().numpy(), box0)
+    if n <= 300:                                                                   # and against the oracle
+        for i in range(0, n, max(1, n // 40)):
+            c, p, _, _ = np_oracle.classify_vec(feats[i], w, b)
+            assert c == cls1[i] and np.abs(p - probs1[i]).max() <= PROB_ATOL
+            assert tuple(box1[i]) == np_oracle.bbox_vec(feats[i], c, w)[0]
+    if n in (65, 297):                                                             # per-layer kernels + standalone tail
+        cls5, probs5, box5 = a.infer_batch(imgs, direct=True)
+        assert np.array_equal(cls0, cls5) and np.array_equal(probs0, probs5) and np.array_equal(box0, box5)
+    a.close()
+
+
+def test_fused_tail_many_classes_and_saturated_maps(shipped_weights):
+    """16 classes (kMaxClasses), 1 class, and feature maps with saturated / dead channels through the fused tail."""
+    import fpga_cnn_b200 as fc
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    for n_cls, shifts in ((16, (2, 4, 6)), (1, (7, 10, 11)), (6, (0, 0, 0)), (6, (31, 31, 31))):
+        w, b = inputs.make_fc(seed=80 + n_cls, n_cls=n_cls)
+        a.load_classifier(w, b)
+        a.set_shifts(*shifts)
+        imgs = inputs.make_images(("rng", 3000 + n_cls), 200)
+        feats = a.run_batch(imgs).reshape(200, 64, 256)
+        cls, probs, box = a.infer_batch(imgs)
+        assert probs.shape == (200, n_cls)
+        for i in range(0, 200, 7):
+            c, p, _, _ = np_oracle.classify_vec(feats[i], w, b)
+            assert c == cls[i] and np.abs(p - probs[i]).max() <= PROB_ATOL, (n_cls, shifts, i)
+            assert tuple(box[i]) == np_oracle.bbox_vec(feats[i], c, w)[0], (n_cls, shifts, i)
     a.close()

@@ -10,6 +10,11 @@ acc = fc.CNNAccelerator(device=0)
 acc.load_weights(wt)
 n = 148 * int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 6
 imgs = torch.randint(0, 256, (n, 128, 128), dtype=torch.uint8, device="cuda")
-acc.run_batch(imgs)
+if len(sys.argv) > 2 and sys.argv[2] == "infer":          # the kTail instantiation: role 4 = tail warp 0
+    import inputs
+    acc.load_classifier(*inputs.make_fc())
+    acc.infer_batch(imgs)
+else:
+    acc.run_batch(imgs)
 acc.synchronize()
 torch.cuda.synchronize()
