@@ -119,7 +119,7 @@ cam_bbox_upsampled_kernel(const uint8_t* __restrict__ feats, const float* __rest
     m = s_red[0];
 #pragma unroll
     for (int w8 = 1; w8 < 8; w8++) m = fmaxf(m, s_red[w8]);
-    if (m > 0.f) cam = __fdiv_rn(cam, m);
+    if (m > 0.f) cam = div_rn_zero_ok(cam, m);
     s_q[py][px] = (uint8_t)(int)__fmul_rn(cam, 255.0f);               // astype(uint8): truncation, value in 0..255
     __syncthreads();
 

@@ -34,4 +34,14 @@ __device__ __forceinline__ uint32_t act_pack4(int v0, int v1, int v2, int v3, in
 }
 __device__ __forceinline__ int max4(int a, int b, int c, int d) { return max(max(a, b), max(c, d)); }
 
+// IEEE round-to-nearest a / b for operands where a is OFTEN EXACTLY ZERO (ReLU outputs, empty pooling bins).  The
+// compiler's division tests its operands with FCHK and sends the whole warp through a ~45-instruction subroutine when any
+// lane's dividend is zero: ncu showed every one of the tail's 20 divisions per thread taking it (profiles/
+// r2_fusedtail_v1_*: 11 k of 21 k clk per image).  A harmless dividend for those lanes keeps the warp on the short
+// inline path; no result changes.
+__device__ __forceinline__ float div_rn_zero_ok(float a, float b) {
+    const float q = __fdiv_rn(a == 0.f ? b : a, b);
+    return a == 0.f ? 0.f : q;
+}
+
 }  // namespace cnnacc

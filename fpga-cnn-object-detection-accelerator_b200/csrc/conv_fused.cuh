@@ -18,10 +18,12 @@
 // a block of 16 row-pairs x 8 column-pairs.
 //   layer 1: one MMA row = one 2x2 POOLING WINDOW.  N = 128 = 4 window members x 32 out-channels, and the B
 //            operand is the 3x3 kernel Toeplitz-expanded over the window's 4x4 input patch: 8 K-slabs of
-//            (2 adjacent pixels x 16 ch), LBO = parity-plane stride.  8 MMAs per 128 windows: 56 % of the MAC
-//            slots are useful, but an M=128, K=32 i8 MMA from shared memory costs max(N/2, 32 + N/4) clk
-//            (profiles/r1_probe_umma_rate.txt: N=32 -> 40, N=128 -> 64), so 64 x 64 = 4.1 k clk per image beats
-//            the 160 x 40 = 6.4 k of one N=32 MMA per tap pair.
+//            (2 adjacent pixels x 16 ch), LBO = parity-plane stride.  An M=128, K=32 i8 MMA from shared memory
+//            costs max(N/2, 32 + N/4) clk (profiles/r1_probe_umma_rate.txt: N=32 -> 40, N=64 -> 48, N=128 -> 64),
+//            which beats the 160 x 40 = 6.4 k clk of one N=32 MMA per tap pair.  Patch row 0 only reaches the
+//            window's upper members and patch row 3 only its lower ones, so those four slabs are N = 64 MMAs
+//            into the matching half of the accumulator columns: 8 tiles x (4 x 64 + 4 x 48) = 3.6 k clk per
+//            image, 64 % of the MAC slots useful, and the operand is 24 KiB instead of 32.
 //            All four members of a window land in one TMEM lane: the pool is thread-local.
 //   layer 2: one MMA row = one output pixel of ONE parity (y%2, x%2); K=32 = one tap over both 16-channel
 //            planes (LBO = plane stride), 9 MMAs, N = 64; the four parities go to four TMEM column groups.
@@ -35,8 +37,11 @@
 //   warps 16-19  epilogues : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
 //   warp 20      tcgen05 MMA issue (whole warp walks the schedule, one elected lane issues), TMEM allocation,
 //                TMA loads (weights once, then images two ahead)
-//   warps 21-22  (kTail instantiation only) the classifier / CAM-box tail of tail.cuh on the layer-2 staging buffer of the
-//                image the epilogue warps have just finished: predictions leave the SM, the feature map need not
+//   warps 24-27  (kTail instantiation only; warps 21-23 idle) the classifier / CAM-box tail of tail.cuh on the layer-2
+//                staging buffer of the image the epilogue warps have just finished: predictions leave the SM, the feature
+//                map need not.  28 warps only fit because the two light warpgroups (20-23, 24-27) hand registers to the
+//                five heavy ones with setmaxnreg: the kernel launches at 72 registers per thread (7 warps x 72 x 32 = 16 128
+//                of a sub-partition's 16 384), then warps 0-19 grow to 80 and warps 20-27 shrink to 48.
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
@@ -61,8 +66,9 @@ constexpr int kA2Q       = 17 * 16;                   // act2 parity-plane strid
 constexpr int kA2P       = 2 * kA2Q;                  // act2 row pitch             (544)
 constexpr int kA2C       = 34 * kA2P;                 // act2 channel-block plane   (18496)
 constexpr int kA2Bytes   = 2 * kA2C;                  // 36992
-constexpr int kB1Slab    = 4096;                      // layer-1 B: one K=32 slab x N=128
-constexpr int kB1Bytes   = 8 * kB1Slab;               // 8 slabs (4 patch rows x 2 column pairs)
+constexpr int kB1Slab    = 4096;                      // layer-1 B: one K=32 slab x N=128 (patch rows 1, 2)
+constexpr int kB1Half    = 2048;                      // ... x N=64 (patch row 0: upper window members; row 3: lower)
+constexpr int kB1Bytes   = 4 * kB1Slab + 4 * kB1Half; // 24576: [r1s0][r1s1][r2s0][r2s1] [r0s0][r0s1][r3s0][r3s1]
 constexpr int kB2Bytes   = 9 * 2048;                  // layer-2 B: 9 taps x (2 K-halves x 8 row groups x 128 B)
 constexpr int kStageBytes = 16384;                    // one image's features, CHW, for the TMA store
 
@@ -76,12 +82,13 @@ constexpr int kOffStage = kOffB2 + kB2Bytes;          // 199680
 constexpr int kOffBar   = kOffStage + kStageBytes;    // 216064
 constexpr int kOffTail  = kOffBar + 256;              // scratch of the two tail warps (tail.cuh)
 #ifdef CNNACC_TRACE
-constexpr int kTailWRows = 2;                         // the trace build's static buffers take 4 KiB
+constexpr int kTailWRows = 4;                         // the trace build's static buffers take 4 KiB
 #else
-constexpr int kTailWRows = 3;                         // classifier rows kept in shared memory (the rest: __ldg through L1)
+constexpr int kTailWRows = 5;                         // classifier rows kept in shared memory (the rest: __ldg through L1)
 #endif
 constexpr int kOffTailW = kOffTail + kTailScratchBytes;
 constexpr int kFusedSmem = kOffTailW + kTailWRows * 4096;   // 229888 <= 232448
+static_assert(kFusedSmem <= 232448, "shared memory plan exceeds 227 KB");
 
 // Optional schedule trace (tools only, -DCNNACC_TRACE): CTA 0 records clock() at pipeline events in shared memory and
 // prints them at exit (tools/trace_run.py).
@@ -121,7 +128,10 @@ constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // mul
 static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
 constexpr int kWarpMma = kL0Warps + kEpiWarps;       // the last warp: MMA issue and TMA loads
 constexpr int kFusedThreads = (kWarpMma + 1) * 32;    // 21 warps = 672
-constexpr int kTailWarps = kTailThreads / 32;         // + 2 warps in the kTail instantiation: 23 warps, still <= 6 per sub-partition
+constexpr int kTailWarps = kTailThreads / 32;         // 4 tail warps = warpgroup 6 of the kTail instantiation
+constexpr int kWarpTail0 = 24;                        // first tail warp (warpgroup aligned: setmaxnreg acts on warpgroups)
+constexpr int kTailKernelThreads = (kWarpTail0 + kTailWarps) * 32;   // 896
+static_assert(kWarpMma == 20 || kWarpMma == 24, "register hand-over below assumes warpgroups 0-4 heavy, 5-6 light");
 constexpr uint32_t kTmemCols = 512;
 #ifndef CNNACC_WAIT_BUDGET_CLK
 #define CNNACC_WAIT_BUDGET_CLK 8000000000LL            // bounded pipeline waits: ~4 s of SM clocks
@@ -180,11 +190,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+#ifndef CNNACC_TRYWAIT_HINT
+#define CNNACC_TRYWAIT_HINT 20000
+#endif
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    // the suspend-time hint lets the hardware park the warp instead of burning issue slots the dp4a warps need
+#if CNNACC_TRYWAIT_HINT > 0
+    // with a suspend-time hint: SYNCS.TRYWAIT; NANOSLEEP.SYNCS hint; SYNCS.PHASECHK (the sleep ends on any barrier event)
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)CNNACC_TRYWAIT_HINT) : "memory");
+#else
+    // plain SYNCS.TRYWAIT: the hardware holds the warp until this barrier's phase completes or its own time limit passes
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok;
 }
 // Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.  Every try_wait parks the warp in
@@ -251,6 +270,17 @@ __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t byt
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory"); }
+// Staging-buffer hand-over between the epilogue warps and the tail warps (kTail): hardware named barriers, so the waiting
+// side costs no issue slots at all (an mbarrier wait polls, and NANOSLEEP.SYNCS wakes on every barrier event of the CTA:
+// ncu counted ~100 wake-ups per image per waiting warp).  The two barriers strictly alternate -- full(k), free(k),
+// full(k+1) ... -- and both sides run the same n_local iterations, so arrivals can never run a phase ahead.
+constexpr int kNamedStageFull = 3, kNamedStageFree = 4;
+__device__ __forceinline__ void stage_bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kEpiWarps * 32 + kTailThreads) : "memory");
+}
+__device__ __forceinline__ void stage_bar_arrive(int id) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "n"(kEpiWarps * 32 + kTailThreads) : "memory");
+}
 
 // Warp-level int8 MMA for layer 0 (K = 9 is too thin for a 128-row tcgen05 tile without a re-layout pass):
 // D(16x8,s32) += A(16x16,u8) * B(16x8,s8).  Fragments (lane = 4*g + t): a0/a1 = rows g / g+8, k = 4t..4t+3;
@@ -277,11 +307,11 @@ __device__ __forceinline__ int wrap24(int v) { return (int)((unsigned)v << 8) >>
 // kWin = window mode (FusedParams::win_*): a separate instantiation, so the 128x128 path carries none of its code.
 // kTail = two more warps run the classifier / CAM-box tail on each image's staged features (tail.cuh).
 template <bool kWin, bool kTail>
-__global__ void __launch_bounds__(kFusedThreads + (kTail ? kTailThreads : 0), 1)
+__global__ void __launch_bounds__(kTail ? kTailKernelThreads : kFusedThreads, 1)
 conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ FusedParams P)
 {
     static_assert(!(kWin && kTail), "the tail needs a whole 16x16 map in the staging buffer");
-    constexpr int kThreads = kFusedThreads + (kTail ? kTailThreads : 0);
+    constexpr int kThreads = kTail ? kTailKernelThreads : kFusedThreads;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bars = s_base + kOffBar;
@@ -324,6 +354,11 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    if constexpr (kTail) {
+        // register hand-over (see the warp-role table): the light warpgroups release first, the heavy ones then grow
+        if (warp >= kWarpMma) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        else                  asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    }
 
     auto wait_or_flag = [&](uint32_t b, uint32_t parity, int code) {
         if (mbar_try(b, parity)) return;                 // fast path: already complete
@@ -553,8 +588,8 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             } else if (k > 0) {                          // the previous image's store and its tail must be done with staging
                 if (P.out && e == 0 && lane == 0) bulk_store_wait_read();
                 if (e == 0) TRACE(1, 70);
-                if constexpr (kTail) wait_or_flag(bar(kBarStageFree), (uint32_t)(k - 1) & 1, kErrStageTimeout);
-                epi_bar_sync();
+                if constexpr (kTail) stage_bar_sync(kNamedStageFree);        // the tail has released the previous image's map
+                else epi_bar_sync();
                 if (e == 0) TRACE(1, 71);
             }
 #pragma unroll 1
@@ -613,8 +648,7 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
             if (!win) {
                 if constexpr (kTail) {                   // hand the staged map to the tail warps
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarStageFull));
+                    stage_bar_arrive(kNamedStageFull);
                     if (e == 0) TRACE(1, 72);
                 }
                 if (P.out) {
@@ -673,11 +707,18 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 if (elect_one()) {
                     const uint32_t d = tm + h * 256;
                     const uint64_t a0 = umma_desc(s_base + kOffA1 + (32 * ty) * kA1P + (8 * tx) * 16, kA1Q, 2 * kA1P);
-                    const uint64_t b0 = umma_desc(s_base + kOffB1, 2048, 128);
+                    const uint64_t bw = umma_desc(s_base + kOffB1, 2048, 128);                 // N = 128 slabs
+                    const uint64_t bn = umma_desc(s_base + kOffB1 + 4 * kB1Slab, 1024, 128);   // N = 64 slabs
 #pragma unroll
-                    for (int sl = 0; sl < 8; sl++) {
-                        const int r = sl >> 1, sx = sl & 1;
-                        umma_i8(d, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), b0 + (uint64_t)((sl * kB1Slab) >> 4), idesc1, sl > 0);
+                    for (int q = 0; q < 4; q++) {        // patch rows 1, 2 reach all four window members; the first overwrites
+                        const int r = 1 + (q >> 1), sx = q & 1;
+                        umma_i8(d, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4), bw + (uint64_t)((q * kB1Slab) >> 4), idesc1, q > 0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {        // patch row 0 -> upper members (columns 0-63), row 3 -> lower (64-127)
+                        const int r = (q >> 1) ? 3 : 0, sx = q & 1;
+                        umma_i8(d + (uint32_t)(q >> 1) * 64u, a0 + (uint64_t)((r * kA1P + sx * 16) >> 4),
+                                bn + (uint64_t)((q * kB1Half) >> 4), idesc2, 1);
                     }
                     umma_commit(bar(kBarTmFull0 + h));
                     if (t == 3) umma_commit(bar(kBarA1TopFree));
@@ -716,18 +757,17 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             }
         }
         TRACE_END(0);
-    } else if constexpr (kTail) {
+    } else if (kTail && warp >= kWarpTail0) {
         // =============== tail warps: staged features -> class / probabilities / CAM box (tail.cuh) =================
-        const int T = (warp - kWarpMma - 1) * 32 + lane;
+        const int T = (warp - kWarpTail0) * 32 + lane;
         TailScratch* sc = reinterpret_cast<TailScratch*>(smem + kOffTail);
         const TailWeights W = tail_stage_weights(reinterpret_cast<float*>(smem + kOffTailW), kTailWRows, P.tail, T);
         tail_bar(2);
         for (int k = 0; k < n_local; k++) {
             const int img = (int)blockIdx.x + k * (int)gridDim.x;
-            wait_or_flag(bar(kBarStageFull), (uint32_t)k & 1, kErrStageTimeout);
+            stage_bar_sync(kNamedStageFull);
             tail_image(smem + kOffStage, sc, T, 2, P.tail, W, (size_t)img, [&] {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarStageFree));
+                if (k + 1 < n_local) stage_bar_arrive(kNamedStageFree);    // the epilogue only waits for it before the next image
             }, [&](int code) { if (T == 0) TRACE(4, code); (void)code; });
         }
         if (T == 0) TRACE_END(4);
@@ -803,17 +843,25 @@ inline void fused_pack_weights(const uint8_t* wbin, uint32_t w0[16][6], uint32_t
             w0[o][dy] = lo;
             w0[o][3 + dy] = lo << 8;
         }
-    // layer 1 (Toeplitz over a 2x2 pooling window): slab sl = (patch row r = sl/2, column pair sx = sl%2), K byte
-    // k = jx*16 + ic is patch pixel (r, 2*sx + jx) channel ic, N row n = (py*2 + px)*32 + oc is window member (py,px):
+    // layer 1 (Toeplitz over a 2x2 pooling window): slab (patch row r, column pair sx), K byte k = jx*16 + ic is patch
+    // pixel (r, 2*sx + jx) channel ic, N row n = (py*2 + px)*32 + oc is window member (py,px):
     //   B[n][k] = w1[oc][ic][r - py][2*sx + jx - px]   when both tap indices are in 0..2, else 0
-    // stored K-major: sl*4096 + (k/16)*2048 + (n/8)*128 + (n%8)*16 + k%16
+    // Patch rows 1, 2 reach both window rows: N = 128 slabs, K-major, at ((r-1)*2 + sx)*4096 + (k/16)*2048 + (n/8)*128 +
+    // (n%8)*16 + k%16.  Patch row 0 only reaches py = 0 and patch row 3 only py = 1 (the other half would be all zero):
+    // N = 64 slabs over n' = n % 64 at 16384 + ((r==3)*2 + sx)*2048 + (k/16)*1024 + (n'/8)*128 + (n'%8)*16 + k%16.
     for (int sl = 0; sl < 8; sl++)
         for (int n = 0; n < 128; n++)
             for (int kk = 0; kk < 32; kk++) {
                 const int r = sl >> 1, sx = sl & 1, py = n >> 6, px = (n >> 5) & 1, oc = n & 31, jx = kk >> 4, ic = kk & 15;
                 const int dy = r - py, dx = 2 * sx + jx - px;
                 if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
-                b1[sl * kB1Slab + jx * 2048 + (n / 8) * 128 + (n % 8) * 16 + ic] = weight_byte(wbin, 1, oc, ic, dy * 3 + dx);
+                const uint8_t wv = weight_byte(wbin, 1, oc, ic, dy * 3 + dx);
+                if (r == 1 || r == 2) {
+                    b1[((r - 1) * 2 + sx) * kB1Slab + jx * 2048 + (n / 8) * 128 + (n % 8) * 16 + ic] = wv;
+                } else {
+                    const int nn = n & 63;               // r == 0 -> py == 0, r == 3 -> py == 1
+                    b1[4 * kB1Slab + ((r == 3 ? 2 : 0) + sx) * kB1Half + jx * 1024 + (nn / 8) * 128 + (nn % 8) * 16 + ic] = wv;
+                }
             }
     // layer 2: tap t, K = input channel; B[n][k] at t*2048 + (k/16)*1024 + (n/8)*128 + (n%8)*16 + k%16
     for (int t = 0; t < 9; t++)
@@ -900,7 +948,7 @@ inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const C
     P.status = fw.d_status; P.status_host = fw.h_status_dev;
     const int grid = (int)std::min<int64_t>(n, sm_count);
     if (win)       conv_stack_fused_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
-    else if (tail) conv_stack_fused_kernel<false, true><<<grid, kFusedThreads + kTailThreads, kFusedSmem, stream>>>(map, P);
+    else if (tail) conv_stack_fused_kernel<false, true><<<grid, kTailKernelThreads, kFusedSmem, stream>>>(map, P);
     else           conv_stack_fused_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
     return (int)cudaGetLastError();
 }

@@ -1,8 +1,8 @@
 // tail.cuh -- follow-on stage: 4x4 spatial-bin pool -> linear -> softmax -> argmax -> CAM bbox.
 //
-// tail_image(): 64 threads (two warps) take one 64x16x16 u8 feature map that sits in SHARED memory (CHW, 16 KiB) to its
+// tail_image(): 128 threads (four warps) take one 64x16x16 u8 feature map that sits in SHARED memory (CHW, 16 KiB) to its
 // 44 bytes of predictions.  It has two callers:
-//   * conv_fused.cuh: two extra warps of the conv-stack kernel run it on the layer-2 staging buffer while the tensor
+//   * conv_fused.cuh: four extra warps of the conv-stack kernel run it on the layer-2 staging buffer while the tensor
 //     core and the epilogue warps are already busy with the next image -- the features never leave the SM and, when the
 //     caller passes no feature pointer, HBM sees 44 B per image instead of 16 KiB out + 16 KiB back in;
 //   * classify_bbox_kernel below (features-in entry point, cnnacc_classify_batch): eight such groups per CTA.
@@ -16,8 +16,8 @@
 // Numerics:
 //   * bin sums are exact integers; pooled = S / 4080 in one rounding (identical to Classifier.classify's
 //     mean-then-/255, pynq_inference.py:325-334; within 1 ulp of classify_vec's /255-then-mean);
-//   * logits: fp32, fixed summation tree (4 bins per task, 4 tasks per thread in order, warp shuffle tree, two warp
-//     partials, bias last);
+//   * logits: fp32, fixed summation tree (4 bins per task, 2 tasks per thread in order, warp shuffle tree, four warp
+//     partials pairwise, bias last);
 //   * CAM: products and sums rounded separately (no FMA) in channel order 0..63, as numpy's reduction over
 //     the outer axis does, so the bbox integers match bit for bit given the same class;
 //   * percentile(70) of 256 values = index 178.5 -> hi - (hi-lo)*0.5 in fp32 (numpy _lerp with t = 0.5).
@@ -27,7 +27,7 @@
 namespace cnnacc {
 
 constexpr int kMaxClasses = 16;
-constexpr int kTailThreads = 64;                // threads that cooperate on one image
+constexpr int kTailThreads = 128;               // threads (four warps) that cooperate on one image
 
 struct TailArgs {
     const float* fc_w;                          // [n_cls][1024] row-major
@@ -40,52 +40,57 @@ struct TailArgs {
     const int32_t* cls_in;                      // [n] or null: bbox_vec's cls_idx argument (CNNACC_FLAG_CLS_GIVEN)
 };
 
-struct __align__(16) TailScratch {              // per 64-thread group
-    float sort[256];                            // one cross-warp exchange of the bitonic sort
-    float part[2][kMaxClasses];                 // per-warp logit partials
-    unsigned long long valid[2];                // per warp: bit ch = channel ch is not saturated (mean <= 250)
-    float red[2];
+struct __align__(16) TailScratch {              // per 128-thread group
+    float sort[2][256];                         // cross-warp exchanges of the bitonic sort (two buffers, used alternately)
+    float part[4][kMaxClasses];                 // per-warp logit partials
+    unsigned long long valid[4];                // per warp: bit ch = channel ch is not saturated (mean <= 250)
+    float red[4];
     float thr;
     int pad;
-    int box[2][4];
+    int box[4][4];
 };
-constexpr int kTailScratchBytes = 1280;
+constexpr int kTailScratchBytes = 2560;
 static_assert(sizeof(TailScratch) <= kTailScratchBytes, "tail scratch");
 
 __device__ __forceinline__ void tail_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kTailThreads) : "memory"); }
 
-// u8 -> f32 through the 2^23 mantissa trick: one PRMT builds 0x4B0000bb, one FADD removes 2^23 (exact for 0..255)
-// instead of a quarter-rate I2F.
-template <int kByte>
-__device__ __forceinline__ float byte_to_float(uint32_t word) {
-    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440 + kByte)), 8388608.0f);
-}
-
-// Classifier rows the tail keeps in shared memory.  The rows do not depend on the image, but a 64-thread group cannot
-// hold its 96 weights per thread in registers, and from global memory every image pays L2 latency for them: next to
-// 217 KB of shared memory the SM's L1 is 28 KB and held only 69 % of the 24 KiB (ncu, profiles/r2_fusedtail_v1_*),
-// which made the logits 11 k of the tail's 21 k clk per image.  Rows that do not fit stay on the __ldg path.
+// Classifier rows the tail keeps in shared memory.  The rows do not depend on the image, but from global memory every image
+// pays L2 latency for them: next to 217 KB of shared memory the SM's L1 is 28 KB and held only 69 % of the 24 KiB (ncu,
+// profiles/r2_fusedtail_v1_*).  Rows that do not fit stay on the __ldg path.
 struct TailWeights {
-    const float* smem;                          // [rows][1024] in shared memory (may be null)
+    uint32_t smem;                              // shared-space address of [rows][1024] floats (explicit ld.shared: a pointer that
+                                                // may be shared or global turns every load into a slow generic LD)
     int rows;
     float bias;                                 // fc_b[lane] for lane < n_cls, read once per kernel
 };
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 
-// Copies min(n_cls, max_rows) classifier rows into shared memory; call with all 64 threads of the group, then tail_bar.
+// Copies min(n_cls, max_rows) classifier rows into shared memory; call with all threads of the group, then tail_bar.
 __device__ __forceinline__ TailWeights tail_stage_weights(float* dst, int max_rows, const TailArgs& A, const int T) {
     TailWeights W;
     W.rows = min(A.n_cls, max_rows);
-    W.smem = dst;
+    W.smem = (uint32_t)__cvta_generic_to_shared(dst);
     for (int i = T; i < W.rows * 256; i += kTailThreads)
         reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(A.fc_w) + i);
     W.bias = (T & 31) < A.n_cls ? __ldg(A.fc_b + (T & 31)) : 0.f;
     return W;
 }
 
-// T = 0..63 within the group; bar_id = a named barrier reserved for these 64 threads; release() is called by every thread
-// after its last read of `stg` (the fused kernel hands the staging buffer back to the epilogue warps there).
 struct TailNoTrace { __device__ __forceinline__ void operator()(int) const {} };
+struct TailTrue { static constexpr bool value = true; };
+struct TailFalse { static constexpr bool value = false; };
 
+// T = 0..127 within the group; bar_id = a named barrier reserved for these 128 threads; release() is called by every thread
+// after its last read of `stg` (the fused kernel hands the staging buffer back to the epilogue warps there).
 template <typename Release, typename Trace = TailNoTrace>
 __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, TailScratch* sc, const int T, const int bar_id,
                                            const TailArgs& A, const TailWeights& W, const size_t img, Release release,
@@ -95,13 +100,13 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     const int lane = T & 31, w = T >> 5;
     const unsigned full = 0xffffffffu;
 
-    // ---- bin sums: task q = T + 64 i owns channel q/4, bin-row q%4 = four 16-byte map rows (64 contiguous bytes, read in a
+    // ---- bin sums: task q = T + 128 i owns channel q/4, bin-row q%4 = four 16-byte map rows (64 contiguous bytes, read in a
     // per-lane rotated order so that the eight lanes of a 128-bit wavefront hit eight different 16-byte bank groups) ----
-    int S[4][4];
+    int S[2][4];
     unsigned long long vbits = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint4* p = reinterpret_cast<const uint4*>(stg + (T + 64 * i) * 64);
+    for (int i = 0; i < 2; i++) {
+        const uint4* p = reinterpret_cast<const uint4*>(stg + (T + 128 * i) * 64);
         S[i][0] = S[i][1] = S[i][2] = S[i][3] = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -115,31 +120,32 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
         int cs = S[i][0] + S[i][1] + S[i][2] + S[i][3];
         cs += __shfl_xor_sync(full, cs, 1);
         cs += __shfl_xor_sync(full, cs, 2);
-        // lanes 4q..4q+3 of warp w hold channel 16 i + 8 w + q: squeeze ballot bits 0,4,..,28 into one byte
+        // lanes 4q..4q+3 of warp w hold channel 32 i + 8 w + q: squeeze ballot bits 0,4,..,28 into one byte
         uint32_t b = __ballot_sync(full, cs <= 250 * 256) & 0x11111111u;
         b = (b | (b >> 3)) & 0x03030303u;
         b = (b | (b >> 6)) & 0x000F000Fu;
         b = (b | (b >> 12)) & 0xFFu;
-        vbits |= (unsigned long long)b << (16 * i + 8 * w);
+        vbits |= (unsigned long long)b << (32 * i + 8 * w);
     }
-    if (lane == 0) sc->valid[w] = vbits;                  // each warp knows half of the channels
+    if (lane == 0) sc->valid[w] = vbits;                  // each warp knows a quarter of the channels
     trace(2);
 
     // ---- logits: W row-major [n_cls][1024]; task q covers bins 4q .. 4q+3 ----
-    float pooled[4][4];
+    float pooled[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) pooled[i][c] = __fdiv_rn((float)S[i][c], 4080.0f);
+        for (int c = 0; c < 4; c++) pooled[i][c] = div_rn_zero_ok((float)S[i][c], 4080.0f);
 #pragma unroll 2
     for (int k = 0; k < A.n_cls; k++) {
         const bool in_smem = k < W.rows;                  // uniform
-        const float4* wr = reinterpret_cast<const float4*>((in_smem ? W.smem : A.fc_w) + (size_t)k * 1024) + T;
+        const float4* wr = reinterpret_cast<const float4*>(A.fc_w + (size_t)k * 1024) + T;
+        const uint32_t ws = W.smem + (uint32_t)(k * 4096 + T * 16);
         float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 2; i++) {
             float4 wv;
-            if (in_smem) wv = wr[64 * i]; else wv = __ldg(wr + 64 * i);
+            if (in_smem) wv = lds_f32x4(ws + 2048 * i); else wv = __ldg(wr + 128 * i);
             float p = pooled[i][0] * wv.x;
             p = fmaf(pooled[i][1], wv.y, p);
             p = fmaf(pooled[i][2], wv.z, p);
@@ -155,7 +161,7 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
 
     // ---- softmax / argmax: every warp computes it (no second barrier), warp 0 writes ----
     float logit = -INFINITY;
-    if (lane < A.n_cls) logit = (sc->part[0][lane] + sc->part[1][lane]) + W.bias;
+    if (lane < A.n_cls) logit = ((sc->part[0][lane] + sc->part[1][lane]) + (sc->part[2][lane] + sc->part[3][lane])) + W.bias;
     float mx = logit;
     int arg = lane < A.n_cls ? lane : 0x7fffffff;
 #pragma unroll
@@ -164,12 +170,14 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
         const int   oa = __shfl_xor_sync(full, arg, off);
         if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }   // first maximum, like np.argmax
     }
-    const float e = lane < A.n_cls ? expf(logit - mx) : 0.f;
-    float sum = e;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(full, sum, off);
     if (w == 0) {
-        if (A.probs && lane < A.n_cls) A.probs[img * A.n_cls + lane] = A.want_logits ? logit : __fdiv_rn(e, sum);
+        if (A.probs) {
+            const float e = lane < A.n_cls ? expf(logit - mx) : 0.f;
+            float sum = e;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(full, sum, off);
+            if (lane < A.n_cls) A.probs[img * A.n_cls + lane] = A.want_logits ? logit : div_rn_zero_ok(e, sum);
+        }
         if (lane == 0 && A.cls_out && !A.cls_in) A.cls_out[img] = arg;
     }
     if (!A.bbox_out) {                                    // uniform: a kernel argument
@@ -181,99 +189,102 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     // bbox_vec takes the class as an argument (realtime_detect.py:85); cls_in carries it when given
     const int cls = A.cls_in ? min(max(A.cls_in[img], 0), A.n_cls - 1) : arg;
 
-    // ---- CAM: thread T owns pixels 4T .. 4T+3 = row T/4, columns 4(T%4) .. +3, all in bin (T/16, T%4), so one class weight
-    // and one 32-bit feature word per channel serve four pixels.  Saturated channels contribute w = 0. ----
-    const unsigned long long valid = sc->valid[0] | sc->valid[1];
+    // ---- CAM: thread T owns pixels 2T, 2T+1 = row T/8, columns 2(T%8), +1, both in bin (T/32, (T%8)/2), so one class weight and
+    // one 16-bit feature load per channel serve two pixels.  Saturated channels contribute w = 0.  u8 -> f32 and the product in
+    // ONE rounding: x = 0x4B0000bb is the float 2^23 + b, and fma(w, x, -w * 2^23) rounds the exact w * b -- the same value as
+    // fmul_rn(w, float(b)) -- so a pixel-channel costs one PRMT, one FFMA and the separately rounded FADD numpy's reduction does.
+    const unsigned long long valid = (sc->valid[0] | sc->valid[1]) | (sc->valid[2] | sc->valid[3]);
     const bool cam_smem = cls < W.rows;                   // uniform: every thread has the same class
-    const float* wc = (cam_smem ? W.smem : A.fc_w) + (size_t)cls * 1024 + (T >> 4) * 4 + (T & 3);
-    const uint32_t* fwp = reinterpret_cast<const uint32_t*>(stg) + T;
-    float cam[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 16
-    for (int ch = 0; ch < 64; ch++) {
-        float wv;
-        if (cam_smem) wv = wc[ch * 16]; else wv = __ldg(wc + ch * 16);
-        wv = ((valid >> ch) & 1ull) ? wv : 0.f;
-        const uint32_t word = fwp[ch * 64];
-        cam[0] = __fadd_rn(cam[0], __fmul_rn(wv, byte_to_float<0>(word)));
-        cam[1] = __fadd_rn(cam[1], __fmul_rn(wv, byte_to_float<1>(word)));
-        cam[2] = __fadd_rn(cam[2], __fmul_rn(wv, byte_to_float<2>(word)));
-        cam[3] = __fadd_rn(cam[3], __fmul_rn(wv, byte_to_float<3>(word)));
-    }
+    const int woff = cls * 1024 + (T >> 5) * 4 + ((T & 7) >> 1);
+    const float* wc = A.fc_w + woff;
+    const uint32_t wcs = W.smem + 4u * (uint32_t)woff;
+    const uint16_t* fwp = reinterpret_cast<const uint16_t*>(stg) + T;
+    float cam[2] = {0.f, 0.f};
+    auto cam_pass = [&](auto from_smem) {                 // 4 x 16 channels: constant offsets inside, one mask word per block
+#pragma unroll 1
+        for (int o = 0; o < 4; o++) {
+            const uint32_t vm = (uint32_t)(valid >> (16 * o));
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const int ch = 16 * o + c;
+                float wv = decltype(from_smem)::value ? lds_f32(wcs + 64u * (uint32_t)ch) : __ldg(wc + ch * 16);
+                wv = ((vm >> c) & 1u) ? wv : 0.f;
+                const float cc = __fmul_rn(wv, -8388608.0f);   // exact
+                const uint32_t word = fwp[ch * 128];
+                cam[0] = __fadd_rn(cam[0], __fmaf_rn(wv, __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7440)), cc));
+                cam[1] = __fadd_rn(cam[1], __fmaf_rn(wv, __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7441)), cc));
+            }
+        }
+    };
+    if (cam_smem) cam_pass(TailTrue()); else cam_pass(TailFalse());
     release();                                            // last read of the feature map
     trace(5);
-#pragma unroll
-    for (int b = 0; b < 4; b++) cam[b] = fmaxf(cam[b], 0.f);
+    cam[0] = fmaxf(cam[0], 0.f);
+    cam[1] = fmaxf(cam[1], 0.f);
 
-    float m = fmaxf(fmaxf(cam[0], cam[1]), fmaxf(cam[2], cam[3]));
+    float m = fmaxf(cam[0], cam[1]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, off));
     if (lane == 0) sc->red[w] = m;
     tail_bar(bar_id);                                     // #2
-    m = fmaxf(sc->red[0], sc->red[1]);
+    m = fmaxf(fmaxf(sc->red[0], sc->red[1]), fmaxf(sc->red[2], sc->red[3]));
     if (m > 0.f) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) cam[b] = __fdiv_rn(cam[b], m);
+        cam[0] = div_rn_zero_ok(cam[0], m);
+        cam[1] = div_rn_zero_ok(cam[1], m);
     }
 
-    // ---- 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort of element e = 4T + b:
-    // strides 1, 2 stay inside the thread, 4..64 are warp shuffles (lane ^ stride/4), 128 is one exchange through
-    // shared memory. ----
+    // ---- 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort of element e = 2T + b:
+    // stride 1 stays inside the thread, 2..32 are warp shuffles (lane ^ stride/2), 64 and 128 are exchanges through shared
+    // memory (three in all). ----
     trace(6);
-    float v[4] = {cam[0], cam[1], cam[2], cam[3]};
+    float v0 = cam[0], v1 = cam[1];
+    int xbuf = 0;
 #pragma unroll
     for (int k = 2; k <= 256; k <<= 1) {
-        const bool up = (k == 2) ? true : (k == 256 ? true : ((T & (k >> 2)) == 0));   // k == 2: decided per pair below
+        const bool up = (k == 256) ? true : ((T & (k >> 1)) == 0);
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j == 128) {
-                reinterpret_cast<float4*>(sc->sort)[T] = make_float4(v[0], v[1], v[2], v[3]);
-                tail_bar(bar_id);                         // #3
-                const float4 o = reinterpret_cast<const float4*>(sc->sort)[T ^ 32];
-                const bool lower = (T & 32) == 0;         // k = 256: every block ascends
-                v[0] = lower ? fminf(v[0], o.x) : fmaxf(v[0], o.x);
-                v[1] = lower ? fminf(v[1], o.y) : fmaxf(v[1], o.y);
-                v[2] = lower ? fminf(v[2], o.z) : fmaxf(v[2], o.z);
-                v[3] = lower ? fminf(v[3], o.w) : fmaxf(v[3], o.w);
-            } else if (j >= 4) {
-                const bool keep_min = (((T & (j >> 2)) == 0) == up);
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const float o = __shfl_xor_sync(full, v[b], j >> 2);
-                    v[b] = keep_min ? fminf(v[b], o) : fmaxf(v[b], o);
-                }
+            if (j >= 64) {
+                reinterpret_cast<float2*>(sc->sort[xbuf])[T] = make_float2(v0, v1);
+                tail_bar(bar_id);
+                const float2 o = reinterpret_cast<const float2*>(sc->sort[xbuf])[T ^ (j >> 1)];
+                xbuf ^= 1;
+                const bool keep_min = (((T & (j >> 1)) == 0) == up);
+                v0 = keep_min ? fminf(v0, o.x) : fmaxf(v0, o.x);
+                v1 = keep_min ? fminf(v1, o.y) : fmaxf(v1, o.y);
+            } else if (j >= 2) {
+                const bool keep_min = (((T & (j >> 1)) == 0) == up);
+                const float o0 = __shfl_xor_sync(full, v0, j >> 1), o1 = __shfl_xor_sync(full, v1, j >> 1);
+                v0 = keep_min ? fminf(v0, o0) : fmaxf(v0, o0);
+                v1 = keep_min ? fminf(v1, o1) : fmaxf(v1, o1);
             } else {
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    if (a & j) continue;
-                    const bool asc = (k == 2) ? ((a & 2) == 0) : up;
-                    const float lo = fminf(v[a], v[a | j]), hi = fmaxf(v[a], v[a | j]);
-                    v[a] = asc ? lo : hi;
-                    v[a | j] = asc ? hi : lo;
-                }
+                const float lo = fminf(v0, v1), hi = fmaxf(v0, v1);
+                v0 = up ? lo : hi;
+                v1 = up ? hi : lo;
             }
         }
     }
     trace(7);
-    if (T == 44) {                                        // elements 178, 179 = thread 44, b = 2, 3
-        const float lo = v[2], hi = v[3];
-        float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
+    if (T == 89) {                                        // elements 178, 179 = thread 89, b = 0, 1
+        float thr = __fsub_rn(v1, __fmul_rn(__fsub_rn(v1, v0), 0.5f));
         sc->thr = (0.25f > thr) ? 0.25f : thr;            // python max(p, 0.25)
     }
-    tail_bar(bar_id);                                     // #4
+    tail_bar(bar_id);                                     // #3
     const float thr = sc->thr;
-    const int x0 = 4 * (T & 3), y = T >> 2;
+    const int x0 = 2 * (T & 7), y = T >> 3;
     int xmin = 16, xmax = -1;
-#pragma unroll
-    for (int b = 0; b < 4; b++)
-        if (cam[b] > thr) { xmin = min(xmin, x0 + b); xmax = max(xmax, x0 + b); }
+    if (cam[0] > thr) { xmin = x0; xmax = x0; }
+    if (cam[1] > thr) { xmin = min(xmin, x0 + 1); xmax = x0 + 1; }
     int ymin = xmax >= 0 ? y : 16, ymax = xmax >= 0 ? y : -1;
     xmin = __reduce_min_sync(full, xmin); ymin = __reduce_min_sync(full, ymin);
     xmax = __reduce_max_sync(full, xmax); ymax = __reduce_max_sync(full, ymax);
     if (lane == 0) { sc->box[w][0] = xmin; sc->box[w][1] = ymin; sc->box[w][2] = xmax; sc->box[w][3] = ymax; }
-    tail_bar(bar_id);                                     // #5
+    tail_bar(bar_id);                                     // #4
     if (T == 0) {
-        xmin = min(sc->box[0][0], sc->box[1][0]); ymin = min(sc->box[0][1], sc->box[1][1]);
-        xmax = max(sc->box[0][2], sc->box[1][2]); ymax = max(sc->box[0][3], sc->box[1][3]);
+        xmin = min(min(sc->box[0][0], sc->box[1][0]), min(sc->box[2][0], sc->box[3][0]));
+        ymin = min(min(sc->box[0][1], sc->box[1][1]), min(sc->box[2][1], sc->box[3][1]));
+        xmax = max(max(sc->box[0][2], sc->box[1][2]), max(sc->box[2][2], sc->box[3][2]));
+        ymax = max(max(sc->box[0][3], sc->box[1][3]), max(sc->box[2][3], sc->box[3][3]));
         int4 bx;
         if (xmax >= 0) bx = make_int4(xmin * 8, ymin * 8, min(127, (xmax + 1) * 8), min(127, (ymax + 1) * 8));
         else bx = make_int4(0, 0, 127, 127);
@@ -282,8 +293,8 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     trace(8);
 }
 
-// Features-in entry point (cnnacc_classify_batch): persistent CTAs of eight 64-thread groups; a group copies its image's
-// 16 KiB map into its own shared-memory slot (16 independent 128-bit loads per thread) and runs tail_image on it.
+// Features-in entry point (cnnacc_classify_batch): persistent CTAs of eight 128-thread groups; a group copies its image's
+// 16 KiB map into its own shared-memory slot (8 independent 128-bit loads per thread) and runs tail_image on it.
 constexpr int kTailGroups = 8;
 constexpr int kTailSmemW = kMaxClasses * 4096;          // every classifier row, shared by the eight groups
 constexpr int kTailSmem = kTailGroups * (16384 + kTailScratchBytes) + kTailSmemW;
@@ -292,24 +303,24 @@ __global__ void __launch_bounds__(kTailGroups * kTailThreads, 1)
 classify_bbox_kernel(const uint8_t* __restrict__ feats, long long n, const TailArgs A)
 {
     extern __shared__ __align__(16) uint8_t tail_smem[];
-    const int g = threadIdx.x >> 6, T = threadIdx.x & 63;
+    const int g = threadIdx.x / kTailThreads, T = threadIdx.x % kTailThreads;
     uint8_t* stg = tail_smem + g * 16384;
     TailScratch* sc = reinterpret_cast<TailScratch*>(tail_smem + kTailGroups * 16384 + g * kTailScratchBytes);
     float* wsm = reinterpret_cast<float*>(tail_smem + kTailGroups * (16384 + kTailScratchBytes));
-    // group g stages rows g, g+8 (every group ends with the same view after the CTA barrier)
+    // all threads stage the n_cls classifier rows once per CTA
     for (int i = threadIdx.x; i < A.n_cls * 256; i += kTailGroups * kTailThreads)
         reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(A.fc_w) + i);
     TailWeights W;
-    W.smem = wsm; W.rows = A.n_cls;
+    W.smem = (uint32_t)__cvta_generic_to_shared(wsm); W.rows = A.n_cls;
     W.bias = (T & 31) < A.n_cls ? __ldg(A.fc_b + (T & 31)) : 0.f;
     __syncthreads();
     for (long long img = (long long)blockIdx.x * kTailGroups + g; img < n; img += (long long)gridDim.x * kTailGroups) {
         const uint4* src = reinterpret_cast<const uint4*>(feats + (size_t)img * 16384);
-        uint4 v[16];
+        uint4 v[8];
 #pragma unroll
-        for (int r = 0; r < 16; r++) v[r] = __ldcs(src + T + 64 * r);       // read once: streaming
+        for (int r = 0; r < 8; r++) v[r] = __ldcs(src + T + kTailThreads * r);       // read once: streaming
 #pragma unroll
-        for (int r = 0; r < 16; r++) reinterpret_cast<uint4*>(stg)[T + 64 * r] = v[r];
+        for (int r = 0; r < 8; r++) reinterpret_cast<uint4*>(stg)[T + kTailThreads * r] = v[r];
         tail_bar(1 + g);
         tail_image(stg, sc, T, 1 + g, A, W, (size_t)img, [] {});
         tail_bar(1 + g);                                  // every thread is done with stg before it is overwritten
@@ -336,8 +347,8 @@ pool_features_kernel(const uint8_t* __restrict__ feats, float* __restrict__ pool
         S[3] = __dp4a(v.w, 0x01010101u, (unsigned)S[3]);
     }
     reinterpret_cast<float4*>(pooled + img * 1024)[t] =
-        make_float4(__fdiv_rn((float)S[0], 4080.0f), __fdiv_rn((float)S[1], 4080.0f),
-                    __fdiv_rn((float)S[2], 4080.0f), __fdiv_rn((float)S[3], 4080.0f));
+        make_float4(div_rn_zero_ok((float)S[0], 4080.0f), div_rn_zero_ok((float)S[1], 4080.0f),
+                    div_rn_zero_ok((float)S[2], 4080.0f), div_rn_zero_ok((float)S[3], 4080.0f));
 }
 
 }  // namespace cnnacc

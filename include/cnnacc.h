@@ -84,9 +84,9 @@ int cnnacc_get_accumulator_bits(const cnnacc_handle *h);
 /* Host-only view of the one-off weight permutation (parse_kernels, arm_cnn.c:43-59, hoisted out of the
  * per-image path): weights.bin -> the fused kernel's operand images.  No GPU needed; tests/ re-derive the conv
  * from these buffers to pin the packed layouts.  w0: 96 dp4a words
- * [oc][lo0..2,hi0..2] followed by 256 layer-0 mma.sync B-fragment words [block][lane]; b1: 32768 B; b2: 18432 B. */
+ * [oc][lo0..2,hi0..2] followed by 256 layer-0 mma.sync B-fragment words [block][lane]; b1: 24576 B; b2: 18432 B. */
 #define CNNACC_PACK_W0_WORDS 352
-#define CNNACC_PACK_B1_BYTES 32768
+#define CNNACC_PACK_B1_BYTES 24576
 #define CNNACC_PACK_B2_BYTES 18432
 int cnnacc_pack_weights_host(const uint8_t *weights_bin, size_t n, uint32_t *w0, uint8_t *b1, uint8_t *b2);
 

@@ -23,13 +23,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # constants mirrored from conv_fused.cuh
 A1Q, A1P = 33 * 16, 2 * 33 * 16
 A2Q, A2P, A2C = 17 * 16, 2 * 17 * 16, 34 * 2 * 17 * 16
-B1_SLAB = 4096
+B1_SLAB, B1_HALF = 4096, 2048
 
 
 def pack(weights):
     lib = fc.load()
     w0 = np.zeros(352, np.uint32)
-    b1 = np.zeros(32768, np.uint8)
+    b1 = np.zeros(24576, np.uint8)
     b2 = np.zeros(18432, np.uint8)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     assert lib.cnnacc_pack_weights_host(p(weights), weights.size, p(w0), p(b1), p(b2)) == 0
@@ -99,17 +99,24 @@ def store_act1(l0):
 
 
 def layer1_umma(a1, b1, shift):
-    """8 tiles x 8 Toeplitz K-slabs, N = 128 = 4 window members x 32 oc; pool over the members of a TMEM lane."""
+    """8 tiles x 8 Toeplitz K-slabs, N = 128 = 4 window members x 32 oc; pool over the members of a TMEM lane.
+    The kernel's issue order: patch rows 1, 2 as N = 128 MMAs (the first one overwrites the accumulator), then patch row 0
+    as N = 64 into columns 0-63 and patch row 3 as N = 64 into columns 64-127."""
     out = np.zeros((32, 32, 32), np.uint8)
     for t in range(8):
         ty, tx = t >> 2, t & 3
         a0 = (32 * ty) * A1P + (8 * tx) * 16
-        D = np.zeros((128, 128), np.int64)
-        for sl in range(8):
-            r, sx = sl >> 1, sl & 1
+        D = None
+        for q in range(4):
+            r, sx = 1 + (q >> 1), q & 1
             A = operand(a1, a0 + r * A1P + sx * 16, A1Q, 2 * A1P, 128, signed=False)
-            B = operand(b1, sl * B1_SLAB, 2048, 128, 128, signed=True)
-            D += A @ B.T
+            B = operand(b1, q * B1_SLAB, 2048, 128, 128, signed=True)
+            D = A @ B.T if q == 0 else D + A @ B.T
+        for q in range(4):
+            r, sx = (3 if q >> 1 else 0), q & 1
+            A = operand(a1, a0 + r * A1P + sx * 16, A1Q, 2 * A1P, 128, signed=False)
+            B = operand(b1, 4 * B1_SLAB + q * B1_HALF, 1024, 128, 64, signed=True)
+            D[:, 64 * (q >> 1):64 * (q >> 1) + 64] += A @ B.T
         pooled = D.reshape(128, 4, 32).max(axis=1)                   # lane = window, columns = member*32 + oc
         L = np.arange(128)
         out[:, 16 * ty + (L >> 3), 8 * tx + (L & 7)] = act(pooled, shift).T

@@ -9,3 +9,4 @@ python tools/pipe_timing.py > $OUT/${TAG}_pipe.json 2> $OUT/${TAG}_pipe.err; ech
 if [ -f build/variants/libcnnacc_trace.so ]; then
   CNNACC_LIB_PATH=$PWD/build/variants/libcnnacc_trace.so python tools/trace_run.py 8 infer > $OUT/${TAG}_trace.raw 2>&1; python tools/trace_print.py $OUT/${TAG}_trace.raw > $OUT/${TAG}_trace.txt
 fi
+for v in build/variants/lib_*.so; do [ -f $v ] && CNNACC_LIB_PATH=$PWD/$v python tools/pipe_timing_short.py 2>&1 | tail -1; done
