@@ -10,6 +10,7 @@ CSRC = os.path.join(_DIR, "csrc")
 
 OK, ERR_TIMEOUT, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 FLAG_DEVICE_PTRS, FLAG_DIRECT, FLAG_KEEP_MAPS, FLAG_CLS_GIVEN, FLAG_BBOX_UPSAMPLED, FLAG_LOGITS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+FLAG_TWO_KERNELS = 0x40
 
 # every symbol include/cnnacc.h declares: name -> (restype, argtypes)
 _c = ctypes

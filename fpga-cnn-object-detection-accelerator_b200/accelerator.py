@@ -249,11 +249,11 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_load_classifier(self._h, _vp(fc_w), _vp(fc_b), fc_w.shape[0]))
         self._n_cls = fc_w.shape[0]
 
-    def _predict(self, fn, x, direct=False, bbox="vec", logits=False):
+    def _predict(self, fn, x, direct=False, bbox="vec", logits=False, two_kernels=False):
         if bbox not in ("vec", "upsampled"):
             raise ValueError("bbox must be 'vec' (realtime_detect.bbox_vec) or 'upsampled' (Classifier.get_cam_bbox)")
         flags = (_lib.FLAG_DIRECT if direct else 0) | (_lib.FLAG_BBOX_UPSAMPLED if bbox == "upsampled" else 0) | \
-                (_lib.FLAG_LOGITS if logits else 0)
+                (_lib.FLAG_LOGITS if logits else 0) | (_lib.FLAG_TWO_KERNELS if two_kernels else 0)
         if self._n_cls == 0:
             raise RuntimeError("classifier not loaded")
         if _is_torch_cuda(x):
@@ -324,10 +324,11 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_classify_batch(self._h, _vp(x), n, None, _vp(cls), _vp(bbox), _lib.FLAG_CLS_GIVEN))
         return bbox
 
-    def infer_batch(self, images, direct=False, bbox="vec", logits=False):
+    def infer_batch(self, images, direct=False, bbox="vec", logits=False, two_kernels=False):
         """images [N,128,128] u8 -> (cls, probs, bbox).  The classifier / CAM-box tail runs inside the conv-stack kernel on
-        the feature map still in shared memory: only 44 B of predictions per image reach HBM."""
-        return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox, logits)
+        the feature map still in shared memory: only 44 B of predictions per image reach HBM.  two_kernels=True is the A/B
+        path: features to a workspace, then the features-in tail kernel."""
+        return self._predict(self._libc.cnnacc_infer_batch, images, direct, bbox, logits, two_kernels)
 
     def preprocess(self, frames):
         """realtime_detect.py:582-591 for a batch: frames [N,h,w,3] u8 BGR -> [N,128,128] u8 (centre-crop, BGR2GRAY,

@@ -202,7 +202,7 @@ int launch_tail(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_feats, i
 // the features afterwards (want_feats) or the per-layer kernels are in use.
 int infer_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_imgs, int64_t m, uint8_t* d_feat_ws, bool want_feats,
                  const TailArgs& A, uint32_t flags) {
-    const bool fused_ok = !(flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS)) && h->fused.ready;
+    const bool fused_ok = !(flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS | CNNACC_FLAG_TWO_KERNELS)) && h->fused.ready;
     if (fused_ok) {
         int rc = launch_fused(h->fused, stream, d_imgs, m, want_feats ? d_feat_ws : nullptr, h->shifts, h->sm_count, nullptr, nullptr, &A);
         h->launches++;
@@ -214,7 +214,7 @@ int infer_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_imgs, i
     return launch_tail(h, stream, d_feat_ws, m, A);
 }
 bool infer_needs_feat_ws(const cnnacc_handle* h, bool want_feats, uint32_t flags) {
-    return want_feats || (flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS)) || !h->fused.ready;
+    return want_feats || (flags & (CNNACC_FLAG_DIRECT | CNNACC_FLAG_KEEP_MAPS | CNNACC_FLAG_TWO_KERNELS)) || !h->fused.ready;
 }
 
 // Classifier.get_cam_bbox per image (cam_upsampled.cuh); d_cam may be null
@@ -676,7 +676,8 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
         // one fused launch covers the whole call unless a workspace bounds the chunk
-        const int64_t chunk = feat_ws ? std::min<int64_t>(n, 16384) : n;
+        static const int64_t ws_chunk = [] { const char* e = getenv("CNNACC_WS_CHUNK"); int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 16384); }();
+        const int64_t chunk = feat_ws ? std::min<int64_t>(n, ws_chunk) : n;
         if (feat_ws) {
             if ((rc = grow(h, &h->d_feat, &h->cap_feat, (size_t)chunk * img_sz))) return rc;
             if (maps && (rc = ensure_maps(h, chunk, CNNACC_IMG, CNNACC_IMG))) return rc;

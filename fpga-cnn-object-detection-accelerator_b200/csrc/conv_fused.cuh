@@ -37,11 +37,12 @@
 //   warps 16-19  epilogues : TMEM -> pool -> shift/ReLU/saturate -> act2 (layer 1) / staging -> TMA store (layer 2)
 //   warp 20      tcgen05 MMA issue (whole warp walks the schedule, one elected lane issues), TMEM allocation,
 //                TMA loads (weights once, then images two ahead)
-//   warps 24-27  (kTail instantiation only; warps 21-23 idle) the classifier / CAM-box tail of tail.cuh on the layer-2
-//                staging buffer of the image the epilogue warps have just finished: predictions leave the SM, the feature
-//                map need not.  28 warps only fit because the two light warpgroups (20-23, 24-27) hand registers to the
-//                five heavy ones with setmaxnreg: the kernel launches at 72 registers per thread (7 warps x 72 x 32 = 16 128
-//                of a sub-partition's 16 384), then warps 0-19 grow to 80 and warps 20-27 shrink to 48.
+//   warps 24-27  (kTail instantiation only) front stage of the classifier / CAM-box tail of tail.cuh on the layer-2
+//                staging buffer of the image the epilogue warps have just finished (bin sums, logits, softmax, CAM);
+//   warps 22-23  (kTail; warp 21 idle) its back stage, one image behind (CAM maximum, percentile, box): predictions leave
+//                the SM, the feature map need not.  28 warps only fit because the two light warpgroups (20-23, 24-27) hand
+//                registers to the five heavy ones with setmaxnreg: the kernel launches at 72 registers per thread (7 warps
+//                x 72 x 32 = 16 128 of a sub-partition's 16 384), then warps 0-19 grow to 80 and warps 20-27 shrink to 48.
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
@@ -94,7 +95,7 @@ static_assert(kFusedSmem <= 232448, "shared memory plan exceeds 227 KB");
 // prints them at exit (tools/trace_run.py).
 #ifdef CNNACC_TRACE
 #include <cstdio>
-constexpr int kTraceMax = 110, kTraceRoles = 5;
+constexpr int kTraceMax = 90, kTraceRoles = 6;
 #define TRACE(role, code)                                                                                          \
     do {                                                                                                           \
         if (blockIdx.x == 0 && lane == 0 && trace_n < kTraceMax) {                                                 \
@@ -114,6 +115,9 @@ constexpr int kTraceMax = 110, kTraceRoles = 5;
 #define TRACE_END(role) do { } while (0)
 #endif
 
+#ifndef CNNACC_TAIL_WARPS_FIRST
+#define CNNACC_TAIL_WARPS_FIRST 0
+#endif
 #ifndef CNNACC_L0_DP4A_WARPS
 #define CNNACC_L0_DP4A_WARPS 8     // layer-0 warps that use dp4a; the rest use mma.sync (0 and 16 = the single-pipe ablations)
 #endif
@@ -190,8 +194,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+// 0 = plain try_wait (shipped).  With a suspend-time hint every failed try_wait costs a NANOSLEEP.SYNCS that wakes on ANY
+// barrier event of the CTA (ncu: ~100 wake-ups per image per waiting warp, 16.8 k polling instructions per image in the
+// round-1 kernel); without it the hardware holds the warp on this barrier alone: +2.5-4 % images/s
+// (profiles/r2_trywait_hint_sweep.txt).
 #ifndef CNNACC_TRYWAIT_HINT
-#define CNNACC_TRYWAIT_HINT 20000
+#define CNNACC_TRYWAIT_HINT 0
 #endif
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -275,6 +283,16 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // ncu counted ~100 wake-ups per image per waiting warp).  The two barriers strictly alternate -- full(k), free(k),
 // full(k+1) ... -- and both sides run the same n_local iterations, so arrivals can never run a phase ahead.
 constexpr int kNamedStageFull = 3, kNamedStageFree = 4;
+// ... and the same between the tail's front warps (24-27) and back warps (22-23) for the 1 KiB CAM buffer; 2 and 5 are the
+// front's and the back's own barriers.
+constexpr int kNamedTailFront = 2, kNamedTailBack = 5, kNamedCamFull = 6, kNamedCamFree = 7;
+constexpr int kWarpTailBack0 = 22;
+__device__ __forceinline__ void cam_bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kTailThreads + kTailBackThreads) : "memory");
+}
+__device__ __forceinline__ void cam_bar_arrive(int id) {
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "n"(kTailThreads + kTailBackThreads) : "memory");
+}
 __device__ __forceinline__ void stage_bar_sync(int id) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kEpiWarps * 32 + kTailThreads) : "memory");
 }
@@ -320,7 +338,15 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     int* s_err = reinterpret_cast<int*>(smem + kOffBar + 8 * kNumBars + 8);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform in the compiler's eyes
+    // Role index.  In the kTail instantiation the light roles sit on the LOWEST hardware warp ids (CNNACC_TAIL_WARPS_FIRST):
+    // hardware warps 0-3 = tail front (role 24-27), 4-7 = MMA / idle / tail back (20-23), 8-11 = epilogues (16-19, TMEM
+    // lane quarter = hardware warp % 4 still holds), 12-27 = layer 0 (0-15).  Warpgroups stay aligned for setmaxnreg.
+    const int hw_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform in the compiler's eyes
+#if CNNACC_TAIL_WARPS_FIRST
+    const int warp = !kTail ? hw_warp : (hw_warp < 4 ? hw_warp + 24 : hw_warp < 8 ? hw_warp + 16 : hw_warp < 12 ? hw_warp + 8 : hw_warp - 12);
+#else
+    const int warp = hw_warp;
+#endif
     const int n_local = (P.n_images - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // images of this CTA
 #ifdef CNNACC_TRACE
     __shared__ unsigned trace_buf[kTraceRoles * kTraceMax];
@@ -762,15 +788,36 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         const int T = (warp - kWarpTail0) * 32 + lane;
         TailScratch* sc = reinterpret_cast<TailScratch*>(smem + kOffTail);
         const TailWeights W = tail_stage_weights(reinterpret_cast<float*>(smem + kOffTailW), kTailWRows, P.tail, T);
-        tail_bar(2);
+        tail_bar(kNamedTailFront);
         for (int k = 0; k < n_local; k++) {
             const int img = (int)blockIdx.x + k * (int)gridDim.x;
             stage_bar_sync(kNamedStageFull);
-            tail_image(smem + kOffStage, sc, T, 2, P.tail, W, (size_t)img, [&] {
+            float c0, c1;
+            const bool want_box = tail_front(smem + kOffStage, sc, T, kNamedTailFront, P.tail, W, (size_t)img, c0, c1, [&] {
                 if (k + 1 < n_local) stage_bar_arrive(kNamedStageFree);    // the epilogue only waits for it before the next image
             }, [&](int code) { if (T == 0) TRACE(4, code); (void)code; });
+            if (want_box) {                              // hand the CAM to the back warps (single 1 KiB buffer)
+                if (k > 0) cam_bar_sync(kNamedCamFree);
+                reinterpret_cast<float2*>(sc->cam)[T] = make_float2(c0, c1);
+                cam_bar_arrive(kNamedCamFull);
+            }
         }
         if (T == 0) TRACE_END(4);
+    } else if (kTail && warp >= kWarpTailBack0 && warp < kWarpTail0) {
+        // =============== tail back warps: CAM -> maximum, 70th percentile, box; one image behind the front warps =========
+        if (P.tail.bbox_out) {
+            const int T = (warp - kWarpTailBack0) * 32 + lane;
+            TailScratch* sc = reinterpret_cast<TailScratch*>(smem + kOffTail);
+            for (int k = 0; k < n_local; k++) {
+                const int img = (int)blockIdx.x + k * (int)gridDim.x;
+                cam_bar_sync(kNamedCamFull);
+                const float4 q = reinterpret_cast<const float4*>(sc->cam)[T];
+                float cam[4] = {q.x, q.y, q.z, q.w};
+                if (k + 1 < n_local) cam_bar_arrive(kNamedCamFree);
+                tail_back(cam, sc, T, kNamedTailBack, P.tail, (size_t)img, [&](int code) { if (T == 0) TRACE(5, code); (void)code; });
+            }
+            if (T == 0) TRACE_END(5);
+        }
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------

@@ -27,7 +27,8 @@
 namespace cnnacc {
 
 constexpr int kMaxClasses = 16;
-constexpr int kTailThreads = 128;               // threads (four warps) that cooperate on one image
+constexpr int kTailThreads = 128;               // front stage: four warps (bin sums, logits, softmax, CAM) on one image
+constexpr int kTailBackThreads = 64;            // back stage: two warps (CAM maximum, percentile, box), one image behind
 
 struct TailArgs {
     const float* fc_w;                          // [n_cls][1024] row-major
@@ -40,19 +41,21 @@ struct TailArgs {
     const int32_t* cls_in;                      // [n] or null: bbox_vec's cls_idx argument (CNNACC_FLAG_CLS_GIVEN)
 };
 
-struct __align__(16) TailScratch {              // per 128-thread group
-    float sort[2][256];                         // cross-warp exchanges of the bitonic sort (two buffers, used alternately)
-    float part[4][kMaxClasses];                 // per-warp logit partials
-    unsigned long long valid[4];                // per warp: bit ch = channel ch is not saturated (mean <= 250)
-    float red[4];
+struct __align__(16) TailScratch {              // per group
+    float cam[256];                             // front -> back: the ReLU-ed, not yet normalised CAM of one image
+    float sort[256];                            // back: the one cross-warp exchange of its bitonic sort
+    float part[4][kMaxClasses];                 // front: per-warp logit partials
+    unsigned long long valid[4];                // front, per warp: bit ch = channel ch is not saturated (mean <= 250)
+    float red[2];                               // back
     float thr;
     int pad;
-    int box[4][4];
+    int box[2][4];
 };
 constexpr int kTailScratchBytes = 2560;
 static_assert(sizeof(TailScratch) <= kTailScratchBytes, "tail scratch");
 
 __device__ __forceinline__ void tail_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kTailThreads) : "memory"); }
+__device__ __forceinline__ void tail_back_bar(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kTailBackThreads) : "memory"); }
 
 // Classifier rows the tail keeps in shared memory.  The rows do not depend on the image, but from global memory every image
 // pays L2 latency for them: next to 217 KB of shared memory the SM's L1 is 28 KB and held only 69 % of the 24 KiB (ncu,
@@ -89,12 +92,18 @@ struct TailNoTrace { __device__ __forceinline__ void operator()(int) const {} };
 struct TailTrue { static constexpr bool value = true; };
 struct TailFalse { static constexpr bool value = false; };
 
-// T = 0..127 within the group; bar_id = a named barrier reserved for these 128 threads; release() is called by every thread
-// after its last read of `stg` (the fused kernel hands the staging buffer back to the epilogue warps there).
+// The tail is a two-stage pipeline.  tail_front (128 threads) needs the feature map: bin sums, logits, softmax / argmax and
+// the class activation map, whose two pixels per thread it returns after ReLU.  tail_back (64 threads) needs only those 256
+// floats: maximum, normalisation, 70th percentile, box.  In the fused kernel the two stages run on different warps, one image
+// apart, so the serial chain that holds the staging buffer ends with the CAM.
+//
+// tail_front: T = 0..127 within the group; bar_id = a named barrier reserved for these 128 threads; release() is called by
+// every thread after its last read of `stg` (the fused kernel hands the staging buffer back to the epilogue warps there).
+// Returns false when no box is wanted (cam0 / cam1 are then not written).
 template <typename Release, typename Trace = TailNoTrace>
-__device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, TailScratch* sc, const int T, const int bar_id,
-                                           const TailArgs& A, const TailWeights& W, const size_t img, Release release,
-                                           Trace trace = Trace())
+__device__ __forceinline__ bool tail_front(const uint8_t* __restrict__ stg, TailScratch* sc, const int T, const int bar_id,
+                                           const TailArgs& A, const TailWeights& W, const size_t img, float& cam0, float& cam1,
+                                           Release release, Trace trace = Trace())
 {
     trace(1);
     const int lane = T & 31, w = T >> 5;
@@ -136,25 +145,36 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int c = 0; c < 4; c++) pooled[i][c] = div_rn_zero_ok((float)S[i][c], 4080.0f);
-#pragma unroll 2
-    for (int k = 0; k < A.n_cls; k++) {
-        const bool in_smem = k < W.rows;                  // uniform
-        const float4* wr = reinterpret_cast<const float4*>(A.fc_w + (size_t)k * 1024) + T;
-        const uint32_t ws = W.smem + (uint32_t)(k * 4096 + T * 16);
-        float acc = 0.f;
+    // three classes at a time: their shuffle trees are independent and interleave (one tree is ~150 clk of pure latency)
+    for (int k0 = 0; k0 < A.n_cls; k0 += 3) {
+        float acc[3];
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            float4 wv;
-            if (in_smem) wv = lds_f32x4(ws + 2048 * i); else wv = __ldg(wr + 128 * i);
-            float p = pooled[i][0] * wv.x;
-            p = fmaf(pooled[i][1], wv.y, p);
-            p = fmaf(pooled[i][2], wv.z, p);
-            p = fmaf(pooled[i][3], wv.w, p);
-            acc = i ? acc + p : p;
+        for (int c = 0; c < 3; c++) {
+            const int k = min(k0 + c, A.n_cls - 1);       // the padding classes of the last group recompute the last one
+            const bool in_smem = k < W.rows;              // uniform
+            const float4* wr = reinterpret_cast<const float4*>(A.fc_w + (size_t)k * 1024) + T;
+            const uint32_t ws = W.smem + (uint32_t)(k * 4096 + T * 16);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float4 wv;
+                if (in_smem) wv = lds_f32x4(ws + 2048 * i); else wv = __ldg(wr + 128 * i);
+                float p = pooled[i][0] * wv.x;
+                p = fmaf(pooled[i][1], wv.y, p);
+                p = fmaf(pooled[i][2], wv.z, p);
+                p = fmaf(pooled[i][3], wv.w, p);
+                acc[c] = i ? acc[c] + p : p;
+            }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(full, acc, off);
-        if (lane == 0) sc->part[w][k] = acc;
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] += __shfl_xor_sync(full, acc[c], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (k0 + c < A.n_cls) sc->part[w][k0 + c] = acc[c];
+        }
     }
     trace(3);
     tail_bar(bar_id);                                     // #1: partials and the valid mask are visible
@@ -183,7 +203,7 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     if (!A.bbox_out) {                                    // uniform: a kernel argument
         release();
         tail_bar(bar_id);                                 // everyone has read sc->part before the next image overwrites it
-        return;
+        return false;
     }
     trace(4);
     // bbox_vec takes the class as an argument (realtime_detect.py:85); cls_in carries it when given
@@ -219,72 +239,88 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     if (cam_smem) cam_pass(TailTrue()); else cam_pass(TailFalse());
     release();                                            // last read of the feature map
     trace(5);
-    cam[0] = fmaxf(cam[0], 0.f);
-    cam[1] = fmaxf(cam[1], 0.f);
+    cam0 = fmaxf(cam[0], 0.f);
+    cam1 = fmaxf(cam[1], 0.f);
+    tail_bar(bar_id);                                     // #2: everyone has read sc->part / sc->valid of this image
+    return true;
+}
 
-    float m = fmaxf(cam[0], cam[1]);
+// tail_back: T = 0..63; v[b] = ReLU-ed CAM of pixel 4T + b (row T/4, columns 4(T%4) + b); bar_id = a named barrier reserved for
+// these 64 threads.  Maximum -> normalise -> 70th percentile of the 256 values (index 178.5: sorted[178], sorted[179]) ->
+// threshold -> box.  Bitonic sort of element e = 4T + b: strides 1, 2 stay inside the thread, 4..64 are warp shuffles
+// (lane ^ stride/4), 128 is one exchange through shared memory.
+template <typename Trace = TailNoTrace>
+__device__ __forceinline__ void tail_back(float (&cam)[4], TailScratch* sc, const int T, const int bar_id, const TailArgs& A,
+                                          const size_t img, Trace trace = Trace())
+{
+    const int lane = T & 31, w = T >> 5;
+    const unsigned full = 0xffffffffu;
+    float m = fmaxf(fmaxf(cam[0], cam[1]), fmaxf(cam[2], cam[3]));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(full, m, off));
     if (lane == 0) sc->red[w] = m;
-    tail_bar(bar_id);                                     // #2
-    m = fmaxf(fmaxf(sc->red[0], sc->red[1]), fmaxf(sc->red[2], sc->red[3]));
+    tail_back_bar(bar_id);
+    m = fmaxf(sc->red[0], sc->red[1]);
     if (m > 0.f) {
-        cam[0] = div_rn_zero_ok(cam[0], m);
-        cam[1] = div_rn_zero_ok(cam[1], m);
+#pragma unroll
+        for (int b = 0; b < 4; b++) cam[b] = div_rn_zero_ok(cam[b], m);
     }
-
-    // ---- 70th percentile of 256 values = index 178.5: sorted[178] and sorted[179].  Bitonic sort of element e = 2T + b:
-    // stride 1 stays inside the thread, 2..32 are warp shuffles (lane ^ stride/2), 64 and 128 are exchanges through shared
-    // memory (three in all). ----
     trace(6);
-    float v0 = cam[0], v1 = cam[1];
-    int xbuf = 0;
+    float v[4] = {cam[0], cam[1], cam[2], cam[3]};
 #pragma unroll
     for (int k = 2; k <= 256; k <<= 1) {
-        const bool up = (k == 256) ? true : ((T & (k >> 1)) == 0);
+        const bool up = (k == 256) ? true : ((T & (k >> 2)) == 0);       // k == 2: decided per pair below
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 64) {
-                reinterpret_cast<float2*>(sc->sort[xbuf])[T] = make_float2(v0, v1);
-                tail_bar(bar_id);
-                const float2 o = reinterpret_cast<const float2*>(sc->sort[xbuf])[T ^ (j >> 1)];
-                xbuf ^= 1;
-                const bool keep_min = (((T & (j >> 1)) == 0) == up);
-                v0 = keep_min ? fminf(v0, o.x) : fmaxf(v0, o.x);
-                v1 = keep_min ? fminf(v1, o.y) : fmaxf(v1, o.y);
-            } else if (j >= 2) {
-                const bool keep_min = (((T & (j >> 1)) == 0) == up);
-                const float o0 = __shfl_xor_sync(full, v0, j >> 1), o1 = __shfl_xor_sync(full, v1, j >> 1);
-                v0 = keep_min ? fminf(v0, o0) : fmaxf(v0, o0);
-                v1 = keep_min ? fminf(v1, o1) : fmaxf(v1, o1);
+            if (j == 128) {
+                reinterpret_cast<float4*>(sc->sort)[T] = make_float4(v[0], v[1], v[2], v[3]);
+                tail_back_bar(bar_id);
+                const float4 o = reinterpret_cast<const float4*>(sc->sort)[T ^ 32];
+                const bool lower = (T & 32) == 0;         // k = 256: every block ascends
+                v[0] = lower ? fminf(v[0], o.x) : fmaxf(v[0], o.x);
+                v[1] = lower ? fminf(v[1], o.y) : fmaxf(v[1], o.y);
+                v[2] = lower ? fminf(v[2], o.z) : fmaxf(v[2], o.z);
+                v[3] = lower ? fminf(v[3], o.w) : fmaxf(v[3], o.w);
+            } else if (j >= 4) {
+                const bool keep_min = (((T & (j >> 2)) == 0) == up);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const float o = __shfl_xor_sync(full, v[b], j >> 2);
+                    v[b] = keep_min ? fminf(v[b], o) : fmaxf(v[b], o);
+                }
             } else {
-                const float lo = fminf(v0, v1), hi = fmaxf(v0, v1);
-                v0 = up ? lo : hi;
-                v1 = up ? hi : lo;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (a & j) continue;
+                    const bool asc = (k == 2) ? ((a & 2) == 0) : up;
+                    const float lo = fminf(v[a], v[a | j]), hi = fmaxf(v[a], v[a | j]);
+                    v[a] = asc ? lo : hi;
+                    v[a | j] = asc ? hi : lo;
+                }
             }
         }
     }
     trace(7);
-    if (T == 89) {                                        // elements 178, 179 = thread 89, b = 0, 1
-        float thr = __fsub_rn(v1, __fmul_rn(__fsub_rn(v1, v0), 0.5f));
+    if (T == 44) {                                        // elements 178, 179 = thread 44, b = 2, 3
+        const float lo = v[2], hi = v[3];
+        float thr = __fsub_rn(hi, __fmul_rn(__fsub_rn(hi, lo), 0.5f));
         sc->thr = (0.25f > thr) ? 0.25f : thr;            // python max(p, 0.25)
     }
-    tail_bar(bar_id);                                     // #3
+    tail_back_bar(bar_id);
     const float thr = sc->thr;
-    const int x0 = 2 * (T & 7), y = T >> 3;
+    const int x0 = 4 * (T & 3), y = T >> 2;
     int xmin = 16, xmax = -1;
-    if (cam[0] > thr) { xmin = x0; xmax = x0; }
-    if (cam[1] > thr) { xmin = min(xmin, x0 + 1); xmax = x0 + 1; }
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (cam[b] > thr) { xmin = min(xmin, x0 + b); xmax = x0 + b; }
     int ymin = xmax >= 0 ? y : 16, ymax = xmax >= 0 ? y : -1;
     xmin = __reduce_min_sync(full, xmin); ymin = __reduce_min_sync(full, ymin);
     xmax = __reduce_max_sync(full, xmax); ymax = __reduce_max_sync(full, ymax);
     if (lane == 0) { sc->box[w][0] = xmin; sc->box[w][1] = ymin; sc->box[w][2] = xmax; sc->box[w][3] = ymax; }
-    tail_bar(bar_id);                                     // #4
+    tail_back_bar(bar_id);
     if (T == 0) {
-        xmin = min(min(sc->box[0][0], sc->box[1][0]), min(sc->box[2][0], sc->box[3][0]));
-        ymin = min(min(sc->box[0][1], sc->box[1][1]), min(sc->box[2][1], sc->box[3][1]));
-        xmax = max(max(sc->box[0][2], sc->box[1][2]), max(sc->box[2][2], sc->box[3][2]));
-        ymax = max(max(sc->box[0][3], sc->box[1][3]), max(sc->box[2][3], sc->box[3][3]));
+        xmin = min(sc->box[0][0], sc->box[1][0]); ymin = min(sc->box[0][1], sc->box[1][1]);
+        xmax = max(sc->box[0][2], sc->box[1][2]); ymax = max(sc->box[0][3], sc->box[1][3]);
         int4 bx;
         if (xmax >= 0) bx = make_int4(xmin * 8, ymin * 8, min(127, (xmax + 1) * 8), min(127, (ymax + 1) * 8));
         else bx = make_int4(0, 0, 127, 127);
@@ -293,10 +329,11 @@ __device__ __forceinline__ void tail_image(const uint8_t* __restrict__ stg, Tail
     trace(8);
 }
 
-// Features-in entry point (cnnacc_classify_batch): persistent CTAs of eight 128-thread groups; a group copies its image's
-// 16 KiB map into its own shared-memory slot (8 independent 128-bit loads per thread) and runs tail_image on it.
-constexpr int kTailGroups = 8;
-constexpr int kTailSmemW = kMaxClasses * 4096;          // every classifier row, shared by the eight groups
+// Features-in entry point (cnnacc_classify_batch): persistent CTAs of seven 128-thread groups; a group copies its image's
+// 16 KiB map into its own shared-memory slot (8 independent 128-bit loads per thread), runs tail_front on it, and its first two
+// warps then run tail_back while the other two already fetch the next image.
+constexpr int kTailGroups = 7;                          // 7 x (one 128-thread + one 64-thread named barrier) = 14 of the 15 ids
+constexpr int kTailSmemW = kMaxClasses * 4096;          // every classifier row, shared by the groups
 constexpr int kTailSmem = kTailGroups * (16384 + kTailScratchBytes) + kTailSmemW;
 
 __global__ void __launch_bounds__(kTailGroups * kTailThreads, 1)
@@ -304,6 +341,7 @@ classify_bbox_kernel(const uint8_t* __restrict__ feats, long long n, const TailA
 {
     extern __shared__ __align__(16) uint8_t tail_smem[];
     const int g = threadIdx.x / kTailThreads, T = threadIdx.x % kTailThreads;
+    const int bar_front = 1 + g, bar_back = 1 + kTailGroups + g;
     uint8_t* stg = tail_smem + g * 16384;
     TailScratch* sc = reinterpret_cast<TailScratch*>(tail_smem + kTailGroups * 16384 + g * kTailScratchBytes);
     float* wsm = reinterpret_cast<float*>(tail_smem + kTailGroups * (16384 + kTailScratchBytes));
@@ -319,11 +357,22 @@ classify_bbox_kernel(const uint8_t* __restrict__ feats, long long n, const TailA
         uint4 v[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) v[r] = __ldcs(src + T + kTailThreads * r);       // read once: streaming
+        // (the previous image's tail_front ended with a group barrier after its last read of stg, and its tail_back
+        // threads have read sc->cam before they come back here: both buffers are free)
 #pragma unroll
         for (int r = 0; r < 8; r++) reinterpret_cast<uint4*>(stg)[T + kTailThreads * r] = v[r];
-        tail_bar(1 + g);
-        tail_image(stg, sc, T, 1 + g, A, W, (size_t)img, [] {});
-        tail_bar(1 + g);                                  // every thread is done with stg before it is overwritten
+        tail_bar(bar_front);
+        float c0, c1;
+        const bool want_box = tail_front(stg, sc, T, bar_front, A, W, (size_t)img, c0, c1, [] {});
+        if (want_box) {
+            reinterpret_cast<float2*>(sc->cam)[T] = make_float2(c0, c1);
+            tail_bar(bar_front);
+            if (T < kTailBackThreads) {
+                const float4 q = reinterpret_cast<const float4*>(sc->cam)[T];
+                float cam[4] = {q.x, q.y, q.z, q.w};
+                tail_back(cam, sc, T, bar_back, A, (size_t)img);
+            }
+        }
     }
 }
 

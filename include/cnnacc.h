@@ -47,6 +47,8 @@ extern "C" {
 #define CNNACC_FLAG_CLS_GIVEN     0x8u  /* classify_batch: cls[] is an INPUT (bbox_vec's cls_idx argument), not written */
 #define CNNACC_FLAG_BBOX_UPSAMPLED 0x10u /* classify_batch / infer_batch: bbox = Classifier.get_cam_bbox (pynq_inference.py:349-408:
                                             u8 CAM -> PIL bilinear 16->128 -> percentile / 0.2 floor -> pad 3) instead of bbox_vec */
+#define CNNACC_FLAG_TWO_KERNELS   0x40u /* infer_batch / detect_frames: write the features to a workspace and run the features-in
+                                            tail kernel on them instead of the tail warps inside the conv-stack kernel (A/B path) */
 #define CNNACC_FLAG_LOGITS        0x20u /* classify_batch / infer_batch / detect_frames: probs[] receives the raw fp32 logits
                                             W.pooled + b (realtime_detect.py:79) instead of their softmax -- the quantity the
                                             1e-5-relative parity bar is stated on */

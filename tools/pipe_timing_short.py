@@ -11,7 +11,8 @@ B = 65536
 x = [torch.randint(0, 256, (B, 128, 128), dtype=torch.uint8, device="cuda") for _ in range(2)]
 f = [torch.empty((B, 64, 16, 16), dtype=torch.uint8, device="cuda") for _ in range(2)]
 res = {"lib": os.path.basename(os.environ.get("CNNACC_LIB_PATH", "libcnnacc.so"))}
-for name, fn in (("conv", lambda i: acc.run_batch(x[i % 2], out=f[i % 2])), ("infer", lambda i: acc.infer_batch(x[i % 2]))):
+for name, fn in (("conv", lambda i: acc.run_batch(x[i % 2], out=f[i % 2])), ("infer", lambda i: acc.infer_batch(x[i % 2])),
+                 ("infer_two_kernels", lambda i: acc.infer_batch(x[i % 2], two_kernels=True))):
     for i in range(3): fn(i)
     torch.cuda.synchronize(); acc.timer_start()
     for i in range(10): fn(i)

@@ -2,7 +2,7 @@
 """Merge the per-role TRACE lines of a -DCNNACC_TRACE run into one timeline (cycles since the first event)."""
 import sys
 ev = [l.split() for l in open(sys.argv[1]) if l.startswith("TRACE")]
-names = {0: "MMA", 1: "EPI", 2: "L0a", 3: "L0b", 4: "TAIL"}
+names = {0: "MMA", 1: "EPI", 2: "L0a", 3: "L0b", 4: "TAIL", 5: "BACK"}
 seqs = {}
 for _, r, c, t in ev:
     seqs.setdefault(int(r), []).append((int(c), int(t)))
