@@ -118,6 +118,8 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_synchronize(self._h))
 
     def timer_start(self):
+        """CUDA-event timer on the handle's stream: pair it with use_stream(...) when timing calls on torch tensors (without
+        use_stream those run on torch's current stream, not on the handle's own)."""
         self._check(self._libc.cnnacc_timer_start(self._h))
 
     def timer_stop(self):

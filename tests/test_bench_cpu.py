@@ -64,3 +64,20 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the two arms' `config`: the reference arm must print exactly what our arm prints."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["config"] == bench.ours_config(4096, 1, False, 16)
+    assert "sample" not in line["config"] and "sample" in line["cpu_baseline"]
+
+
+def test_roofline_traffic_comes_from_the_newest_committed_capture():
+    per_image, name = bench.ncu_dram_bytes_per_image()
+    assert name and name.endswith("_ncu_summary.txt") and os.path.exists(os.path.join(ROOT, "profiles", name))
+    assert 16384 <= per_image <= 40000            # one image in, (up to) one feature map out
+    rounds = [int(f[1:f.index("_")]) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_ncu_summary.txt") and f[1].isdigit()]
+    assert name.startswith(f"r{max(rounds)}_") or per_image                        # newest round preferred
