@@ -615,6 +615,31 @@ def run_ours(args, weights):
     acc.run_batch(imgs[0], out=feats[0], direct=args.direct)
     acc.synchronize()
     ok = bool(np.array_equal(h_feats[:64], feats[0][:64].cpu().numpy()))
+    # The ceiling of that leg on THIS box with THIS many ranks copying at once: the same bytes per step as plain concurrent
+    # cudaMemcpyAsync H2D + D2H on two streams (torch copies, no kernels), all ranks together, max over ranks.
+    t_h_in, t_h_out = torch.from_numpy(h_imgs), torch.from_numpy(h_feats)
+    d_in, d_out = imgs[0][:Be], feats[0][:Be]
+    s_in, s_out = torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)
+
+    def raw_copies(reps):
+        for _ in range(reps):
+            with torch.cuda.stream(s_in):
+                d_in.copy_(t_h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                t_h_out.copy_(d_out, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+
+    raw_copies(2)
+    barrier()
+    t0 = time.perf_counter()
+    raw_copies(e2e_steps)
+    raw_s = reduce_max(time.perf_counter() - t0, ddist)
+    raw_ceiling = world * Be * e2e_steps / raw_s
+    h_feats[:] = 0
+    acc.use_stream(None)
+    acc.run_batch(h_imgs, out=h_feats, direct=args.direct)      # (the probe overwrote h_feats with d_out: restore a real result)
+    acc.use_stream(stream.cuda_stream)
 
     # ---- BASELINE configs[3]: the sharded 1M-image stream through the full pipeline, at every N ----
     del imgs[1:], feats[1:]
@@ -757,7 +782,11 @@ def run_ours(args, weights):
             "sustained": sustained,
             "stream_1m": stream_1m,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": Be * 16384, "d2h_bytes_per_step": Be * 16384,
-                    "batch": Be, "steps": e2e_steps, "host_buffers": "pinned (cnnacc_alloc_host)", "cpu_affinity": affinity, "matches_device_run": ok},
+                    "batch": Be, "steps": e2e_steps, "host_buffers": "pinned (cnnacc_alloc_host)", "cpu_affinity": affinity, "matches_device_run": ok,
+                    "raw_copy_ceiling_images_per_s": raw_ceiling, "frac_of_raw_copy_ceiling": e2e_value / raw_ceiling,
+                    "raw_copy_ceiling_note": f"the same {Be * 16384} B H2D + {Be * 16384} B D2H per step as plain concurrent cudaMemcpyAsync on two "
+                                             f"streams from the same pinned buffers, no kernels, all {world} rank(s) at once, max over ranks: "
+                                             f"{raw_ceiling * 16384 / 1e9 / world:.1f} GB/s per direction per GPU"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -23,7 +23,8 @@ namespace {
 
 constexpr int kSlots = 4;                       // staging buffers in flight for host-pointer batches
 constexpr int kSmallN = 64;                     // calls up to this many units skip the staging ring (latency path)
-constexpr size_t kSmallPredBytes = (size_t)kSmallN * (16 + kMaxClasses * 4 + 4);   // bbox | probs | cls
+constexpr size_t kPredBytesPerImage = 16 + kMaxClasses * 4 + 4;   // bbox | probs | cls, sized for the most classes
+constexpr int64_t kPredSuper = 1 << 20;         // host-pointer calls bring predictions back in blocks of up to this many images
 constexpr size_t kBramBytes = 16 * 4096 + 32 * 1024 + 64 * 256;   // 112-channel feature-BRAM mirror
 
 struct Slot {
@@ -60,7 +61,11 @@ struct cnnacc_handle {
     int *d_prep_start = nullptr, *d_prep_cnt = nullptr; float* d_prep_alpha = nullptr; size_t cap_prep_alpha = 0;
     uint8_t* d_gray = nullptr; size_t cap_gray = 0;
     // small calls (<= kSmallN units): everything on one stream, predictions come back in one copy through pinned memory
+    // predictions of a host-pointer call: one device block the kernels write, one pinned block it is copied to in a single
+    // D2H, then plain memcpy into the caller's (usually pageable) arrays.  Copying straight into pageable memory would make
+    // every cudaMemcpyAsync synchronous and stall the H2D ring behind each chunk's kernels (tools/host_fed_probe.py).
     uint8_t *d_pred_small = nullptr, *h_pred_small = nullptr;
+    size_t cap_pred = 0;                            // images the two blocks hold
     // single-image protocol state
     uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned + mapped: the batch-1 path runs zero-copy on them
     uint8_t *h_img_dev = nullptr, *h_bram_dev = nullptr;   // their device addresses
@@ -342,8 +347,9 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer(&h->h_img_dev, h->h_img, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostGetDevicePointer(&h->h_bram_dev, h->h_bram, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
-    if ((e = cudaHostAlloc(&h->h_pred_small, kSmallPredBytes, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
-    if ((e = cudaMalloc(&h->d_pred_small, kSmallPredBytes)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaHostAlloc(&h->h_pred_small, kSmallN * kPredBytesPerImage, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaMalloc(&h->d_pred_small, kSmallN * kPredBytesPerImage)) != cudaSuccess) return bail("cudaMalloc", e);
+    h->cap_pred = kSmallN;
     if ((e = cudaMalloc(&h->d_img1, CNNACC_IMG * CNNACC_IMG)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_bram, kBramBytes)) != cudaSuccess) return bail("cudaMalloc", e);
     *out = h;
@@ -638,6 +644,16 @@ int cnnacc_load_classifier(cnnacc_handle* h, const float* fc_w, const float* fc_
 struct SmallPred {
     float* d_probs; int32_t* d_cls; int32_t* d_bbox; size_t bytes; size_t off_probs, off_cls;
 };
+static int ensure_pred(cnnacc_handle* h, int64_t m) {       // grow the prediction blocks to hold m images
+    if ((size_t)m <= h->cap_pred) return 0;
+    CU(h, cudaStreamSynchronize(h->st_d2h));
+    cudaFree(h->d_pred_small); cudaFreeHost(h->h_pred_small);
+    h->d_pred_small = h->h_pred_small = nullptr; h->cap_pred = 0;
+    CU(h, cudaMalloc(&h->d_pred_small, (size_t)m * kPredBytesPerImage));
+    CU(h, cudaHostAlloc(&h->h_pred_small, (size_t)m * kPredBytesPerImage, cudaHostAllocDefault));
+    h->cap_pred = (size_t)m;
+    return 0;
+}
 static SmallPred small_pred(cnnacc_handle* h, int64_t m) {
     SmallPred p;
     p.off_probs = (size_t)m * 16; p.off_cls = p.off_probs + (size_t)m * h->n_cls * 4; p.bytes = p.off_cls + (size_t)m * 4;
@@ -719,35 +735,40 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
         return src_is_images ? check_fused_status(h) : CNNACC_OK;
     }
     // Same ring as cnnacc_run_batch's host path; only the predictions (44 B per image) come back, so the link carries
-    // H2D traffic alone and the chunks can be a quarter of the call, clamped to 4..32 MiB.
-    const size_t chunk_bytes = std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * img_sz / 4));
-    const int64_t hchunk = std::min<int64_t>(n, (int64_t)(chunk_bytes / img_sz));
+    // H2D traffic alone and the chunks can be a quarter of the call, clamped to 4..32 MiB.  The kernels write the
+    // predictions of up to kPredSuper images into one device block; one D2H into pinned memory ends the block.
+    static const size_t env_chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
+    const size_t chunk_bytes = env_chunk_mb ? (env_chunk_mb << 20)
+                                            : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * img_sz / 4));
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(chunk_bytes / img_sz)));
     if (maps && (rc = ensure_maps(h, hchunk, CNNACC_IMG, CNNACC_IMG))) return rc;
+    if ((rc = ensure_pred(h, std::min<int64_t>(n, kPredSuper)))) return rc;
     int64_t ci = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {
-        const int64_t m = std::min(hchunk, n - i0);
-        Slot& s = h->slots[ci % kSlots];
-        if ((rc = slot_reserve(h, s, hchunk * img_sz, feat_ws ? hchunk * img_sz : 0, hchunk))) return rc;
-        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
-        CU(h, cudaMemcpyAsync(s.d_in, src + i0 * img_sz, m * img_sz, cudaMemcpyHostToDevice, h->st_h2d));
-        if (cls_given) CU(h, cudaMemcpyAsync(s.d_cls, cls + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_h2d));
-        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
-        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
-        const TailArgs A = make_tail(h, s.d_probs, s.d_cls, upsampled ? nullptr : s.d_bbox, cls_given, flags);
-        const uint8_t* f = s.d_in;
-        if (src_is_images) {
-            if ((rc = infer_device(h, h->st_k, s.d_in, m, s.d_out, upsampled, A, flags))) return rc;
-            f = s.d_out;
-        } else if ((rc = launch_tail(h, h->st_k, f, m, A))) return rc;
-        if (upsampled && (rc = launch_cam_upsampled(h, h->st_k, f, m, s.d_cls, s.d_bbox, nullptr))) return rc;
-        CU(h, cudaEventRecord(s.ev_k, h->st_k));
-        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
-        if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
-        if (cls && !cls_given) CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
-        if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+    for (int64_t s0 = 0; s0 < n; s0 += kPredSuper) {
+        const int64_t sn = std::min<int64_t>(kPredSuper, n - s0);
+        const SmallPred p = small_pred(h, sn);
+        for (int64_t i0 = 0; i0 < sn; i0 += hchunk, ci++) {
+            const int64_t m = std::min(hchunk, sn - i0);
+            Slot& s = h->slots[ci % kSlots];
+            if ((rc = slot_reserve(h, s, hchunk * img_sz, feat_ws ? hchunk * img_sz : 0, 0))) return rc;
+            if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_k, 0));      // the kernels that read this slot have ended
+            CU(h, cudaMemcpyAsync(s.d_in, src + (s0 + i0) * img_sz, m * img_sz, cudaMemcpyHostToDevice, h->st_h2d));
+            if (cls_given) CU(h, cudaMemcpyAsync(p.d_cls + i0, cls + s0 + i0, m * sizeof(int32_t), cudaMemcpyHostToDevice, h->st_h2d));
+            CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+            CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+            const TailArgs A = make_tail(h, p.d_probs + i0 * nc, p.d_cls + i0, upsampled ? nullptr : p.d_bbox + i0 * 4, cls_given, flags);
+            const uint8_t* f = s.d_in;
+            if (src_is_images) {
+                if ((rc = infer_device(h, h->st_k, s.d_in, m, s.d_out, upsampled, A, flags))) return rc;
+                f = s.d_out;
+            } else if ((rc = launch_tail(h, h->st_k, f, m, A))) return rc;
+            if (upsampled && (rc = launch_cam_upsampled(h, h->st_k, f, m, p.d_cls + i0, p.d_bbox + i0 * 4, nullptr))) return rc;
+            CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        }
+        CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, h->st_k));
+        CU(h, cudaStreamSynchronize(h->st_k));
+        small_pred_unpack(h, p, sn, probs ? probs + s0 * nc : nullptr, cls ? cls + s0 : nullptr, bbox ? bbox + s0 * 4 : nullptr, cls_given);
     }
-    CU(h, cudaStreamSynchronize(h->st_d2h));
     return src_is_images ? check_fused_status(h) : CNNACC_OK;
 }
 
@@ -890,28 +911,33 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
         if (detect) small_pred_unpack(h, p, n, probs, cls, bbox, false);
         return detect ? check_fused_status(h) : CNNACC_OK;
     }
-    // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot
+    // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot; predictions as in predict_impl
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)16 << 20) / frame_sz)));
+    if (detect && (rc = ensure_pred(h, std::min<int64_t>(n, kPredSuper)))) return rc;
     int64_t ci = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
-        const int64_t m = std::min(hchunk, n - i0);
-        Slot& s = h->slots[ci % kSlots];
-        if ((rc = slot_reserve(h, s, hchunk * frame_sz, hchunk * img_sz, hchunk))) return rc;
-        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
-        CU(h, cudaMemcpyAsync(s.d_in, frames + i0 * frame_sz, m * frame_sz, cudaMemcpyHostToDevice, h->st_h2d));
-        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
-        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
-        if ((rc = launch_preprocess(h, h->st_k, s.d_in, m, fh, fw, s.d_out))) return rc;
-        if (detect && (rc = tail(h->st_k, s.d_out, m, s.d_probs, s.d_cls, s.d_bbox))) return rc;
-        CU(h, cudaEventRecord(s.ev_k, h->st_k));
-        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
-        if (gray128) CU(h, cudaMemcpyAsync(gray128 + i0 * img_sz, s.d_out, m * img_sz, cudaMemcpyDeviceToHost, h->st_d2h));
-        if (detect) {
-            if (probs) CU(h, cudaMemcpyAsync(probs + i0 * nc, s.d_probs, m * nc * sizeof(float), cudaMemcpyDeviceToHost, h->st_d2h));
-            if (cls)   CU(h, cudaMemcpyAsync(cls + i0, s.d_cls, m * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
-            if (bbox)  CU(h, cudaMemcpyAsync(bbox + i0 * 4, s.d_bbox, m * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st_d2h));
+    for (int64_t s0 = 0; s0 < n; s0 += kPredSuper) {
+        const int64_t sn = std::min<int64_t>(kPredSuper, n - s0);
+        const SmallPred p = detect ? small_pred(h, sn) : SmallPred();
+        for (int64_t i0 = 0; i0 < sn; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
+            const int64_t m = std::min(hchunk, sn - i0);
+            Slot& s = h->slots[ci % kSlots];
+            if ((rc = slot_reserve(h, s, hchunk * frame_sz, hchunk * img_sz, 0))) return rc;
+            if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+            CU(h, cudaMemcpyAsync(s.d_in, frames + (s0 + i0) * frame_sz, m * frame_sz, cudaMemcpyHostToDevice, h->st_h2d));
+            CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+            CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+            if ((rc = launch_preprocess(h, h->st_k, s.d_in, m, fh, fw, s.d_out))) return rc;
+            if (detect && (rc = tail(h->st_k, s.d_out, m, p.d_probs + i0 * nc, p.d_cls + i0, p.d_bbox + i0 * 4))) return rc;
+            CU(h, cudaEventRecord(s.ev_k, h->st_k));
+            CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+            if (gray128) CU(h, cudaMemcpyAsync(gray128 + (s0 + i0) * img_sz, s.d_out, m * img_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+            CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
         }
-        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+        if (detect) {
+            CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, h->st_k));
+            CU(h, cudaStreamSynchronize(h->st_k));
+            small_pred_unpack(h, p, sn, probs ? probs + s0 * nc : nullptr, cls ? cls + s0 : nullptr, bbox ? bbox + s0 * 4 : nullptr, false);
+        }
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
     return detect ? check_fused_status(h) : CNNACC_OK;
