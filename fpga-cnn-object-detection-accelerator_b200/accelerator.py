@@ -353,6 +353,30 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_preprocess_bgr(self._h, _vp(frames), n, fh, fw, _vp(out), 0))
         return out
 
+    def image_to_gray128(self, images):
+        """The arithmetic of pynq_inference.load_image_any (:414-425) for decoded images of one size: [N,H,W] (mode L),
+        [N,H,W,3] (RGB) or [N,H,W,4] (RGBA) u8 -> [N,128,128] u8 = PIL convert('L').resize((128,128)), bit-identical to
+        Pillow 12.2 (integer luma, default BICUBIC resampler).  numpy in -> numpy out; torch CUDA tensor in -> tensor out."""
+        if _is_torch_cuda(images):
+            import torch
+            if images.dtype != torch.uint8 or not images.is_contiguous() or images.dim() not in (3, 4):
+                raise ValueError("expected a contiguous uint8 tensor [N,H,W] or [N,H,W,C]")
+            n, H, W = images.shape[:3]
+            C = images.shape[3] if images.dim() == 4 else 1
+            out = torch.empty((n, 128, 128), dtype=torch.uint8, device=images.device)
+            with self._on_stream_of(images):
+                self._check(self._libc.cnnacc_image_to_gray128(self._h, ctypes.c_void_p(images.data_ptr()), n, H, W, C,
+                                                               ctypes.c_void_p(out.data_ptr()), _lib.FLAG_DEVICE_PTRS))
+            return out
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        if images.ndim not in (3, 4):
+            raise ValueError("expected [N,H,W] or [N,H,W,C] images")
+        n, H, W = images.shape[:3]
+        C = images.shape[3] if images.ndim == 4 else 1
+        out = np.empty((n, 128, 128), dtype=np.uint8)
+        self._check(self._libc.cnnacc_image_to_gray128(self._h, _vp(images), n, H, W, C, _vp(out), 0))
+        return out
+
     def detect_frames(self, frames, bbox="vec", return_gray=False):
         """The loop body of realtime_detect.py:582-598 for a batch of camera frames [N,h,w,3] u8 BGR (host array):
         preprocess -> conv stack -> classify -> CAM box on the GPU.  -> (cls, probs, bbox[, gray128])."""
@@ -514,3 +538,99 @@ def bbox_vec(feat_flat, cls_idx, fc_w, fc_b=None):
     feats = np.ascontiguousarray(feat_flat, dtype=np.uint8).reshape(1, 64, 256)
     bbox = acc.bbox_batch(feats, np.array([cls_idx], dtype=np.int32))
     return tuple(int(v) for v in bbox[0])
+
+
+_loader_acc = {}
+
+
+def load_image_any(image_path, acc=None):
+    """pynq_inference.load_image_any (:414-425): `.bin` -> the 16384 raw bytes; any other format -> decoded by PIL on the host
+    (file parsing stays there), then convert('L') + resize((128,128)) on the GPU, bit-identical to Pillow.  -> (16384,) u8.
+    Modes other than L / RGB / RGBA (palette, CMYK, 16-bit ...) are first converted to 'L' by PIL itself."""
+    ext = os.path.splitext(image_path)[1].lower()
+    if ext == '.bin':
+        image = np.fromfile(image_path, dtype=np.uint8)
+        if len(image) != 128 * 128:
+            raise ValueError(f"Expected 16384 bytes, got {len(image)}")
+        return image
+    from PIL import Image
+    img = Image.open(image_path)
+    if img.mode not in ("L", "RGB", "RGBA"):
+        img = img.convert("L")
+    arr = np.asarray(img, dtype=np.uint8)
+    if acc is None:
+        acc = _loader_acc.get("acc")
+        if acc is None:
+            acc = _loader_acc["acc"] = CNNAccelerator()
+    return acc.image_to_gray128(arr[None]).reshape(-1)
+
+
+def train_linear_classifier(features, labels, num_classes, lr=0.01, epochs=1000, val_split=0.2, verbose=True, device=0):
+    """retrain_classifier.train_linear_classifier (:24-124) with the arithmetic on the GPU: softmax cross-entropy with
+    class-balanced sample weights and L2 regularisation, SGD with momentum 0.9, learning rate halved every 300 epochs, the
+    weights with the best validation accuracy (checked at epoch 1 and every 100) returned as (W (C,D), b (C,)).
+
+    `features` is (N, D) float32 -- the pooled (N,1024) vectors of CNNAccelerator.pool_features -- `labels` (N,) int.  The
+    shuffle / split / initialisation use numpy's RandomState(42) exactly as the reference does, so both start from the same
+    point; every step afterwards is the same fp32 operation in the same order (torch on CUDA instead of numpy), so the result
+    differs only by summation order inside the matrix products."""
+    import torch
+    dev = torch.device("cuda", device)
+    features = np.ascontiguousarray(features, dtype=np.float32)
+    labels = np.asarray(labels)
+    N, D = features.shape
+    rng = np.random.RandomState(42)
+    indices = rng.permutation(N)
+    n_val = max(1, int(N * val_split))
+    val_idx, train_idx = indices[:n_val], indices[n_val:]
+    y_train_np, y_val_np = labels[train_idx], labels[val_idx]
+    class_counts = np.bincount(y_train_np, minlength=num_classes).astype(np.float32)
+    class_counts = np.maximum(class_counts, 1)
+    class_weights = (1.0 / class_counts)
+    class_weights = class_weights / class_weights.sum() * num_classes
+    W0 = rng.randn(D, num_classes).astype(np.float32) * 0.01
+    hi = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False                 # plain fp32 products, as numpy
+    try:
+        X_train = torch.from_numpy(features[train_idx]).to(dev)
+        X_val = torch.from_numpy(features[val_idx]).to(dev)
+        y_train = torch.from_numpy(y_train_np.astype(np.int64)).to(dev)
+        y_val = torch.from_numpy(y_val_np.astype(np.int64)).to(dev)
+        sample_weights = torch.from_numpy(class_weights.astype(np.float32)).to(dev)[y_train]
+        W = torch.from_numpy(W0).to(dev)
+        b = torch.zeros(num_classes, dtype=torch.float32, device=dev)
+        vW, vb = torch.zeros_like(W), torch.zeros_like(b)
+        momentum, reg_lambda = 0.9, 0.001
+        N_t = y_train.numel()
+        rows = torch.arange(N_t, device=dev)
+        best_val_acc, best_W, best_b = 0, W.clone(), b.clone()
+        for epoch in range(epochs):
+            logits = X_train @ W + b
+            logits = logits - logits.max(dim=1, keepdim=True).values
+            exp_logits = torch.exp(logits)
+            probs = exp_logits / exp_logits.sum(dim=1, keepdim=True)
+            want_loss = verbose and ((epoch + 1) % 100 == 0 or epoch == 0)
+            if want_loss:
+                loss = (-(torch.log(probs[rows, y_train] + 1e-10)) * sample_weights).mean() + 0.5 * reg_lambda * (W * W).sum()
+            dlogits = probs.clone()
+            dlogits[rows, y_train] -= 1
+            dlogits *= sample_weights[:, None]
+            dlogits /= N_t
+            dW = X_train.T @ dlogits + reg_lambda * W
+            db = dlogits.sum(dim=0)
+            vW = momentum * vW - lr * dW
+            vb = momentum * vb - lr * db
+            W += vW
+            b += vb
+            if (epoch + 1) % 100 == 0 or epoch == 0:
+                train_acc = float(((X_train @ W + b).argmax(dim=1) == y_train).float().mean()) * 100
+                val_acc = float(((X_val @ W + b).argmax(dim=1) == y_val).float().mean()) * 100
+                if val_acc > best_val_acc:
+                    best_val_acc, best_W, best_b = val_acc, W.clone(), b.clone()
+                if verbose:
+                    print(f"  Epoch {epoch+1:4d}: loss={float(loss):.4f} train={train_acc:.1f}% val={val_acc:.1f}%")
+            if (epoch + 1) % 300 == 0:
+                lr *= 0.5
+        return best_W.T.contiguous().cpu().numpy(), best_b.cpu().numpy()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = hi

@@ -14,6 +14,7 @@
 #include "int8_peak_probe.cuh"
 #include "cam_upsampled.cuh"
 #include "preprocess.cuh"
+#include "pil_resize.cuh"
 #include "tiling.cuh"
 #include "weights_pack.h"
 
@@ -60,6 +61,10 @@ struct cnnacc_handle {
     int prep_side = 0; AreaTabHost prep_tab;
     int *d_prep_start = nullptr, *d_prep_cnt = nullptr; float* d_prep_alpha = nullptr; size_t cap_prep_alpha = 0;
     uint8_t* d_gray = nullptr; size_t cap_gray = 0;
+    // load_image_any (pil_resize.cuh): Pillow coefficient tables of the last (H, W) seen, on the device
+    int pil_h = 0, pil_w = 0, pil_kh = 0, pil_kw = 0;
+    int32_t *d_pil_kx = nullptr, *d_pil_bx = nullptr, *d_pil_ky = nullptr, *d_pil_by = nullptr;
+    uint8_t *d_pil_tmp = nullptr, *d_pil_in = nullptr, *d_pil_out = nullptr; size_t cap_pil_tmp = 0, cap_pil_in = 0, cap_pil_out = 0;
     // small calls (<= kSmallN units): everything on one stream, predictions come back in one copy through pinned memory
     // predictions of a host-pointer call: one device block the kernels write, one pinned block it is copied to in a single
     // D2H, then plain memcpy into the caller's (usually pageable) arrays.  Copying straight into pageable memory would make
@@ -68,6 +73,8 @@ struct cnnacc_handle {
     size_t cap_pred = 0;                            // images the two blocks hold
     // single-image protocol state
     uint8_t *h_img = nullptr, *h_bram = nullptr;    // pinned + mapped: the batch-1 path runs zero-copy on them
+    int *h_done = nullptr, *h_done_dev = nullptr;   // mapped completion word of the batch-1 path and its device address
+    int done_seq = 0;
     uint8_t *h_img_dev = nullptr, *h_bram_dev = nullptr;   // their device addresses
     CUtensorMap one_map;                            // tensor map over h_img (1 image), encoded once
     bool one_map_ok = false;
@@ -347,6 +354,9 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     if ((e = cudaHostAlloc(&h->h_bram, kBramBytes, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer(&h->h_img_dev, h->h_img, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostGetDevicePointer(&h->h_bram_dev, h->h_bram, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if ((e = cudaHostAlloc(&h->h_done, 64, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    *h->h_done = 0;
+    if ((e = cudaHostGetDevicePointer(&h->h_done_dev, h->h_done, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostAlloc(&h->h_pred_small, kSmallN * kPredBytesPerImage, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaMalloc(&h->d_pred_small, kSmallN * kPredBytesPerImage)) != cudaSuccess) return bail("cudaMalloc", e);
     h->cap_pred = kSmallN;
@@ -366,10 +376,12 @@ int cnnacc_destroy(cnnacc_handle* h) {
     }
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) if (st) cudaStreamDestroy(st);
     cudaFree(h->d_prep_start); cudaFree(h->d_prep_cnt); cudaFree(h->d_prep_alpha); cudaFree(h->d_gray);
+    cudaFree(h->d_pil_kx); cudaFree(h->d_pil_bx); cudaFree(h->d_pil_ky); cudaFree(h->d_pil_by);
+    cudaFree(h->d_pil_tmp); cudaFree(h->d_pil_in); cudaFree(h->d_pil_out);
     cudaFree(h->d_wdirect); cudaFree(h->d_fcw); cudaFree(h->d_fcb);
     cudaFree(h->d_l0); cudaFree(h->d_l1); cudaFree(h->d_feat); cudaFree(h->d_img1); cudaFree(h->d_bram);
     fused_free(h->fused);
-    cudaFreeHost(h->h_img); cudaFreeHost(h->h_bram); cudaFreeHost(h->h_pred_small); cudaFree(h->d_pred_small);
+    cudaFreeHost(h->h_img); cudaFreeHost(h->h_bram); cudaFreeHost(h->h_done); cudaFreeHost(h->h_pred_small); cudaFree(h->d_pred_small);
     cudaEvent_t evs[] = {h->ev_t0, h->ev_t1, h->ev_a, h->ev_b, h->ev_c, h->ev_done};
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -600,10 +612,26 @@ int cnnacc_infer_one(cnnacc_handle* h, const uint8_t* img, uint8_t* feat, float*
             h->one_map_ok = true;
         }
         uint8_t* l2_dev = h->h_bram_dev + 16 * 4096 + 32 * 1024;
-        rc = launch_fused_map(h->fused, h->stream, h->one_map, 1, l2_dev, h->shifts, h->sm_count, nullptr, nullptr);
+        const int seq = ++h->done_seq;
+        rc = launch_fused_map(h->fused, h->stream, h->one_map, 1, l2_dev, h->shifts, h->sm_count, nullptr, nullptr, nullptr, nullptr,
+                              h->h_done_dev, seq);
         h->launches++;
         if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
-        CU(h, cudaStreamSynchronize(h->stream));
+        // The kernel stores `seq` into a mapped host word after its feature store has landed: spinning on that word skips the
+        // driver's wake-up path of a stream synchronise (~8 us of the ~36).  Bounded: after 2 s fall back to the synchronise.
+        {
+            const volatile int* flag = h->h_done;
+            const auto spin0 = std::chrono::steady_clock::now();
+            for (unsigned it = 0; *flag != seq; it++) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                if ((it & 0xFFFF) == 0xFFFF && std::chrono::steady_clock::now() - spin0 > std::chrono::seconds(2)) {
+                    CU(h, cudaStreamSynchronize(h->stream));
+                    break;
+                }
+            }
+        }
         const auto t1 = std::chrono::steady_clock::now();
         std::memcpy(feat, h_l2, CNNACC_FEAT_BYTES);
         if (conv_ms) *conv_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
@@ -994,6 +1022,59 @@ int cnnacc_register_host(void* p, size_t bytes) {
 int cnnacc_unregister_host(void* p) {
     if (!p) return CNNACC_ERR_ARG;
     return cudaHostUnregister(p) == cudaSuccess ? CNNACC_OK : CNNACC_ERR_CUDA;
+}
+
+int cnnacc_image_to_gray128(cnnacc_handle* h, const uint8_t* img, int64_t n, int H, int W, int C, uint8_t* gray128, uint32_t flags) {
+    int rc;
+    if (!h) return CNNACC_ERR_ARG;
+    if (n < 0 || H < 1 || W < 1 || H > 32768 || W > 32768 || (C != 1 && C != 3 && C != 4) || n > 65535)
+        return fail(h, CNNACC_ERR_ARG, "bad n / size / channels (channels: 1 = L, 3 = RGB, 4 = RGBA; sides up to 32768)");
+    if (n == 0) return CNNACC_OK;
+    if (!img || !gray128) return fail(h, CNNACC_ERR_ARG, "NULL image / output pointer");
+    CU(h, cudaSetDevice(h->device));
+    if (H != h->pil_h || W != h->pil_w) {                // Pillow's coefficient tables depend on the input size
+        CU(h, cudaDeviceSynchronize());
+        const PilTabHost tx = make_pil_tab(W), ty = make_pil_tab(H);
+        for (int32_t** p : {&h->d_pil_kx, &h->d_pil_bx, &h->d_pil_ky, &h->d_pil_by}) { cudaFree(*p); *p = nullptr; }
+        h->pil_h = h->pil_w = 0;
+        CU(h, cudaMalloc(&h->d_pil_kx, tx.k.size() * 4)); CU(h, cudaMalloc(&h->d_pil_bx, tx.bounds.size() * 4));
+        CU(h, cudaMalloc(&h->d_pil_ky, ty.k.size() * 4)); CU(h, cudaMalloc(&h->d_pil_by, ty.bounds.size() * 4));
+        CU(h, cudaMemcpy(h->d_pil_kx, tx.k.data(), tx.k.size() * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_pil_bx, tx.bounds.data(), tx.bounds.size() * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_pil_ky, ty.k.data(), ty.k.size() * 4, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_pil_by, ty.bounds.data(), ty.bounds.size() * 4, cudaMemcpyHostToDevice));
+        h->pil_kw = tx.ksize; h->pil_kh = ty.ksize; h->pil_h = H; h->pil_w = W;
+    }
+    const size_t in_bytes = (size_t)n * H * W * C, out_bytes = (size_t)n * kPilOut * kPilOut;
+    const bool dev = (flags & CNNACC_FLAG_DEVICE_PTRS) != 0;
+    cudaStream_t st = h->stream;
+    const uint8_t* d_in = img;
+    uint8_t* d_out = gray128;
+    if (!dev) {
+        if ((rc = grow(h, &h->d_pil_in, &h->cap_pil_in, in_bytes))) return rc;
+        if ((rc = grow(h, &h->d_pil_out, &h->cap_pil_out, out_bytes))) return rc;
+        CU(h, cudaMemcpyAsync(h->d_pil_in, img, in_bytes, cudaMemcpyHostToDevice, st));
+        d_in = h->d_pil_in; d_out = h->d_pil_out;
+    }
+    const bool need_v = H != kPilOut;
+    // the horizontal pass (or, at W == 128, the plain gray conversion) writes [n][H][128]: the result itself when H == 128
+    uint8_t* d_tmp = d_out;
+    if (need_v) {
+        if ((rc = grow(h, &h->d_pil_tmp, &h->cap_pil_tmp, (size_t)n * H * kPilOut))) return rc;
+        d_tmp = h->d_pil_tmp;
+    }
+    pil_horizontal_kernel<<<dim3((unsigned)H, (unsigned)n), kPilOut, 0, st>>>(d_in, d_tmp, h->d_pil_kx, h->d_pil_bx, h->pil_kw, H, W, C, W == kPilOut);
+    h->launches++;
+    if (need_v) {
+        pil_vertical_kernel<<<dim3(kPilOut, (unsigned)n), kPilOut, 0, st>>>(d_tmp, d_out, h->d_pil_ky, h->d_pil_by, h->pil_kh, H);
+        h->launches++;
+    }
+    CU(h, cudaGetLastError());
+    if (!dev) {
+        CU(h, cudaMemcpyAsync(gray128, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+    }
+    return CNNACC_OK;
 }
 
 int cnnacc_alloc_host(size_t bytes, void** out) {

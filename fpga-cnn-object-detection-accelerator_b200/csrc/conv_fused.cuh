@@ -173,6 +173,8 @@ struct FusedParams {
     uint8_t* dump_l1;            // optional [n][32][32][32]
     int* status;                 // device int, OR-ed error bits
     int* status_host;            // the same in mapped pinned host memory: polled without a CUDA call
+    int* done_flag;              // optional (single-CTA latency path): mapped pinned host word that receives done_seq once the
+    int done_seq;                // last feature store has landed, so the host can spin on it instead of a stream synchronise
     // window mode (images larger than 128x128, tiling.cuh): unit u = window (u % win_ntx, (u / win_ntx) % win_nty) of image
     // u / (win_ntx * win_nty); the TMA box is read straight from the big image at pixel origin 8 * win_g{x,y}[..] (origins are
     // even, so x stays 16-byte aligned).  win_ntx == 0: unit u = image u of an [n][128][128] array.
@@ -684,7 +686,14 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 }
             }
         }
-        if (e == 0 && lane == 0) bulk_store_wait_all();
+        if (e == 0 && lane == 0) {
+            bulk_store_wait_all();
+            if (P.done_flag) {                           // cnnacc_infer_one: one CTA, features in mapped host memory
+                if (*reinterpret_cast<volatile int*>(s_err)) *reinterpret_cast<volatile int*>(P.status_host) = *s_err;
+                __threadfence_system();                  // the feature bytes (and the status) before the flag
+                *reinterpret_cast<volatile int*>(P.done_flag) = P.done_seq;
+            }
+        }
         if (e == 0) TRACE_END(1);
     } else if (warp == kWarpMma) {
         // =============== MMA issue + TMA loads: the whole warp walks the schedule, one elected lane issues ========
@@ -972,8 +981,10 @@ struct FusedWindows {             // window mode: see FusedParams
 };
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
                             const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr,
-                            const TailArgs* tail = nullptr) {
+                            const TailArgs* tail = nullptr, int* done_flag = nullptr, int done_seq = 0) {
     FusedParams P;
+    P.done_flag = (n == 1 && !win && !tail) ? done_flag : nullptr;
+    P.done_seq = done_seq;
     if (win && tail) return (int)cudaErrorInvalidValue;
     if (!tail && !d_feats) return (int)cudaErrorInvalidValue;
     std::memset(&P.tail, 0, sizeof(P.tail));

@@ -162,6 +162,14 @@ int cnnacc_preprocess_bgr(cnnacc_handle *h, const uint8_t *frames, int64_t n, in
 int cnnacc_detect_frames(cnnacc_handle *h, const uint8_t *frames, int64_t n, int fh, int fw, uint8_t *gray128,
                          float *probs, int32_t *cls, int32_t *bbox, uint32_t flags);
 
+/* image_to_gray128: the image-loading step of pynq_inference.py, load_image_any (:414-425), for n decoded images of one size:
+ *                 img [n][H][W][C] u8 with C = 1 (mode L), 3 (RGB) or 4 (RGBA) -> gray128 [n][128][128] u8 =
+ *                 Image.convert('L').resize((128, 128)): Pillow's ITU-R 601 integer luma and its default BICUBIC resampler
+ *                 (22-bit fixed point, horizontal pass then vertical pass), reproduced bit for bit (pinned against Pillow
+ *                 12.2.0).  File decoding itself stays on the host. */
+int cnnacc_image_to_gray128(cnnacc_handle *h, const uint8_t *img, int64_t n, int H, int W, int C,
+                            uint8_t *gray128, uint32_t flags);
+
 /* ---- host memory the DMA engines can stream from (pynq.allocate, realtime_detect.py:293,301) */
 int cnnacc_alloc_host(size_t bytes, void **out);
 int cnnacc_free_host(void *p);

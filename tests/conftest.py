@@ -46,3 +46,13 @@ def prep_golden():
 @pytest.fixture(scope="session")
 def acc24_golden():
     return np.load(os.path.join(GOLDEN, "acc24_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def pil_golden():
+    return np.load(os.path.join(GOLDEN, "pil_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def trainer_golden():
+    return np.load(os.path.join(GOLDEN, "trainer_case.npz"))

@@ -216,3 +216,44 @@ PREP_CASES = [
     dict(name="x1_128", frames=("rng", 58), n=1, h=128, w=160),             # scale 1: gray only
     dict(name="odd_131", frames=("rng", 59), n=1, h=131, w=200),            # scale just above 1
 ]
+
+
+# load_image_any cases pinned by tests/golden/pil_cases.npz (tests/golden/make_pil_golden.py runs the reference's own function on
+# PNG files written from these arrays).  kind: 'L' | 'RGB' | 'RGBA'.
+PIL_CASES = [
+    dict(name="pil_rgb_vga", mode="RGB", images=("smooth", 80), h=480, w=640),
+    dict(name="pil_rgb_rng_small", mode="RGB", images=("rng", 81), h=100, w=37),          # both dimensions enlarged
+    dict(name="pil_l_256", mode="L", images=("rng", 82), h=256, w=256),                   # scale 2
+    dict(name="pil_l_same", mode="L", images=("rng", 83), h=128, w=128),                  # size already right: a copy
+    dict(name="pil_rgb_same", mode="RGB", images=("rng", 84), h=128, w=128),              # gray conversion only
+    dict(name="pil_l_w128", mode="L", images=("smooth", 85), h=333, w=128),               # vertical pass only
+    dict(name="pil_rgb_h128", mode="RGB", images=("rng", 86), h=128, w=300),              # horizontal pass only
+    dict(name="pil_rgba_big", mode="RGBA", images=("smooth", 87), h=1000, w=1500),        # 127-tap windows
+    dict(name="pil_l_strip", mode="L", images=("rng", 88), h=17, w=2000),                 # enlarge one way, shrink the other
+    dict(name="pil_rgb_odd", mode="RGB", images=("edges", 89), h=129, w=127),             # ratios just off 1, saturated blocks
+]
+
+
+def make_pil_image(case):
+    """Seeded decoded image of a PIL case: (h,w) for 'L', (h,w,3) 'RGB', (h,w,4) 'RGBA'."""
+    ch = {"L": 1, "RGB": 3, "RGBA": 4}[case["mode"]]
+    tag, seed = case["images"]
+    h, w = case["h"], case["w"]
+    if tag == "edges":
+        planes = [make_frames(("edges", seed), 1, h, w)[0][..., c % 3] for c in range(ch)]
+    elif tag == "smooth":
+        hh, ww = -(-h // 16) * 16, -(-w // 16) * 16
+        planes = [smooth_images(seed * 5 + c, 1, hh, ww)[0, :h, :w] for c in range(ch)]
+    else:
+        planes = [np.random.default_rng(seed * 5 + c).integers(0, 256, (h, w), dtype=np.uint8) for c in range(ch)]
+    return planes[0] if ch == 1 else np.ascontiguousarray(np.stack(planes, axis=-1))
+
+
+def make_training_set(seed=90, n=300, n_cls=6, noise=0.35):
+    """Seeded (n,1024) f32 pooled-feature vectors in 0..1 with class structure + labels, for the classifier trainer
+    (retrain_classifier.train_linear_classifier); noisy enough that validation accuracy moves during training."""
+    rng = np.random.default_rng(seed)
+    templates = (rng.random((n_cls, 1024)) < 0.08).astype(np.float32) * rng.uniform(0.3, 0.9, (n_cls, 1024)).astype(np.float32)
+    labels = rng.integers(0, n_cls, n).astype(np.int64)
+    x = templates[labels] * rng.uniform(0.2, 1.0, (n, 1)).astype(np.float32) + noise * rng.random((n, 1024)).astype(np.float32)
+    return np.clip(x, 0.0, 1.0).astype(np.float32), labels

@@ -228,3 +228,9 @@ def test_acc24_scalar_kats():
     m = 1 << 23
     wrap = lambda v: ((v + m) % (2 * m)) - m
     assert wrap(500 + 300) == 800 and wrap(m) == -m and wrap(-m - 1) == m - 1 and wrap(288 * 127 * 255) == 288 * 127 * 255 - 2 * m
+
+
+@pytest.mark.parametrize("case", inputs.PIL_CASES, ids=lambda c: c["name"])
+def test_load_image_restatement_matches_reference_fixtures(case, pil_golden):
+    """convert('L') + default-filter resize restated (np_oracle.load_image_array) vs pynq_inference.load_image_any's outputs."""
+    assert np.array_equal(np_oracle.load_image_array(inputs.make_pil_image(case)), pil_golden[case["name"]])
