@@ -284,6 +284,11 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // side costs no issue slots at all (an mbarrier wait polls, and NANOSLEEP.SYNCS wakes on every barrier event of the CTA:
 // ncu counted ~100 wake-ups per image per waiting warp).  The two barriers strictly alternate -- full(k), free(k),
 // full(k+1) ... -- and both sides run the same n_local iterations, so arrivals can never run a phase ahead.
+#ifndef CNNACC_L0_RENDEZVOUS
+#define CNNACC_L0_RENDEZVOUS 1
+#endif
+constexpr int kNamedL0Top = 8, kNamedL0Bot = 9;       // the sixteen layer-0 warps behind one poller (see the layer-0 loop)
+__device__ __forceinline__ void l0_bar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kL0Warps * 32) : "memory"); }
 constexpr int kNamedStageFull = 3, kNamedStageFree = 4;
 // ... and the same between the tail's front warps (24-27) and back warps (22-23) for the 1 KiB CAM buffer; 2 and 5 are the
 // front's and the back's own barriers.
@@ -431,8 +436,22 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
             for (int yp = warp; yp < 64; yp += kL0Warps) {
                 // act1 rows still being read by image k-1's layer-1 MMAs: rows 0-33 by the top tiles, 32-65 by the bottom
                 // ones.  This unit writes row yp+1.
-                if (k > 0 && yp == warp) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                // One warp polls the mbarrier for all sixteen; the others park on a hardware named barrier and cost no issue
+                // slots while they wait.  (ncu, profiles/r2a_conv_*: sixteen warps polling A1TopFree executed 2 166 try_waits
+                // per image -- four pollers per sub-partition next to the one epilogue warp whose progress they wait for.)
+                // Every layer-0 warp reaches each of the two points exactly once per image, so the barriers stay in step.
+                // Measured (tools/pipe_timing_short.py): with the tail warps competing for issue slots the rendezvous is worth
+                // +2.7 % (15.67 -> 16.09 M img/s); without them it costs 9 % (19.73 -> 17.88: the sixteen warps then move in
+                // lockstep behind the slowest), so only the kTail instantiation uses it.
+                constexpr bool kRendezvous = kTail && CNNACC_L0_RENDEZVOUS;
+                if (k > 0 && yp == warp) {
+                    if (!kRendezvous || warp == 0) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if constexpr (kRendezvous) l0_bar_sync(kNamedL0Top);
+                }
+                if (k > 0 && yp >= 31 && yp - kL0Warps < 31) {
+                    if (!kRendezvous || warp == 0) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if constexpr (kRendezvous) l0_bar_sync(kNamedL0Bot);
+                }
                 if (warp == 0) TRACE(2, 1); else if (warp == kL0Warps - 1) TRACE(3, 1);
                 if (use_dp4a) {
                     // ---- dp4a: two adjacent windows per lane (xp = 2*lane, 2*lane+1) so the weight words (uniform

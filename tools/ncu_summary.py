@@ -65,7 +65,8 @@ def main():
         sms = 148
         print(f"\n# derived for {n_img} images per launch")
         print(f"images/s under ncu (cold, serialised): {n_img / t:,.0f}")
-        print(f"DRAM traffic per launch: {rd + wr:,.0f} B = {(rd + wr) / n_img:,.0f} B/image (algorithmic 32768 B/image)")
+        print(f"DRAM traffic per launch: {rd + wr:,.0f} B = {(rd + wr) / n_img:,.0f} B/image (algorithmic 32768 B/image for the conv stack "
+              f"with features out, 16428 B/image predictions only; read {rd / n_img:,.0f} + written {wr / n_img:,.0f})")
         print(f"SM cycles per image per SM: {cyc / (n_img / sms):,.0f}")
     src = ncu_csv(rep, "source")
     if len(src) > 3:
@@ -81,7 +82,7 @@ def main():
             samp[op] += int(r[isamp] or 0)
         tot, ts = sum(ops.values()), max(1, sum(samp.values()))
         print(f"\n# SASS opcode mix (warp-level instructions executed: {tot:,}; stall samples: {ts:,})")
-        for op, c in ops.most_common(22):
+        for op, c in ops.most_common():              # the whole table: UTCIMMA / LDTM / UTMALDG are rare but are the point
             per = f"{c / n_img:10.1f}/image" if n_img else ""
             print(f"{op:12s} {c:14,d} {100 * c / tot:5.1f}% {per}   samples {100 * samp[op] / ts:5.1f}%")
 
