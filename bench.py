@@ -695,14 +695,16 @@ def run_ours(args, weights):
         del big5, out5
         acc.use_stream(None)
         one = h_imgs[0].copy()
-        lat = []
+        lat, lat_c = [], []
         for i in range(2200):
             t0 = time.perf_counter()
-            acc.infer_one(one)
+            _, conv_ms, read_ms = acc.infer_one(one)
             lat.append((time.perf_counter() - t0) * 1e3)
-        lat = sorted(lat[200:])
+            lat_c.append(conv_ms + read_ms)
+        lat, lat_c = sorted(lat[200:]), sorted(lat_c[200:])
         extra["batch1_latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "iterations": len(lat),
-                                      "path": "CNNAccelerator.infer_one: host image in, host features out, zero-copy kernel"}
+                                      "path": "CNNAccelerator.infer_one: host image in, host features out, zero-copy kernel",
+                                      "inside_the_c_call_p50": lat_c[len(lat_c) // 2], "inside_the_c_call_p99": lat_c[int(len(lat_c) * 0.99)]}
         # the real-time loop body for camera-sized frames (realtime_detect.py:582-598): pre-process + conv + classify + box
         acc.use_stream(stream.cuda_stream)           # device-resident leg: launches and timer events on one explicit stream
         vga = torch.randint(0, 256, (1024, 480, 640, 3), dtype=torch.uint8, device="cuda", generator=g)

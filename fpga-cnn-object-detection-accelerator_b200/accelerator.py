@@ -77,6 +77,7 @@ class CNNAccelerator:
         self._out_addr = 0
         self._n_cls = 0
         self._user_stream = 0
+        self._one_ms = (ctypes.byref(ctypes.c_float()), ctypes.byref(ctypes.c_float()))
         self._finalizer = weakref.finalize(self, self._libc.cnnacc_destroy, self._h)
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -399,12 +400,15 @@ class CNNAccelerator:
 
     def infer_one(self, gray128):
         """One image, lowest latency.  -> (feat (64,256) u8, conv_ms, read_ms)."""
-        img = np.ascontiguousarray(gray128, dtype=np.uint8).reshape(-1)
+        img = gray128 if (type(gray128) is np.ndarray and gray128.dtype == np.uint8 and gray128.flags.c_contiguous) \
+            else np.ascontiguousarray(gray128, dtype=np.uint8)
         assert img.size == NUM_IMAGE_BYTES
-        feat = np.empty(N_CH * FM, dtype=np.uint8)
-        c, r = ctypes.c_float(), ctypes.c_float()
-        self._check(self._libc.cnnacc_infer_one(self._h, _vp(img), _vp(feat), ctypes.byref(c), ctypes.byref(r)))
-        return feat.reshape(N_CH, FM), c.value, r.value
+        feat = np.empty((N_CH, FM), dtype=np.uint8)
+        c, r = self._one_ms                     # two c_floats kept for the life of the object (the latency path is host-bound)
+        rc = self._libc.cnnacc_infer_one(self._h, img.ctypes.data, feat.ctypes.data, c, r)
+        if rc:
+            self._check(rc)
+        return feat, c._obj.value, r._obj.value
 
 
 class B200Engine:
