@@ -217,13 +217,17 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     return ok;
 }
 // Bounded wait: a broken pipeline must never hang the GPU.  Returns false on timeout.  Every try_wait parks the warp in
-// hardware for a while, and the clock is only consulted every 32 unsuccessful polls.
+// hardware for a while, and the clock is only consulted every 32 unsuccessful polls.  kSleepNs > 0: a plain nanosleep
+// between polls (for the sixteen layer-0 warps, which otherwise out-poll the one epilogue warp of their sub-partition).
+template <int kSleepNs = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, long long budget) {
     const long long t0 = clock64();
     for (;;) {
 #pragma unroll 1
-        for (int i = 0; i < 32; i++)
+        for (int i = 0; i < 32; i++) {
             if (mbar_try(bar, parity)) return true;
+            if constexpr (kSleepNs > 0) __nanosleep(kSleepNs);
+        }
         if (clock64() - t0 > budget) return false;
     }
 }
@@ -284,6 +288,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // side costs no issue slots at all (an mbarrier wait polls, and NANOSLEEP.SYNCS wakes on every barrier event of the CTA:
 // ncu counted ~100 wake-ups per image per waiting warp).  The two barriers strictly alternate -- full(k), free(k),
 // full(k+1) ... -- and both sides run the same n_local iterations, so arrivals can never run a phase ahead.
+#ifndef CNNACC_L0_WAIT_SLEEP_NS
+#define CNNACC_L0_WAIT_SLEEP_NS 0
+#endif
 #ifndef CNNACC_L0_RENDEZVOUS
 #define CNNACC_L0_RENDEZVOUS 1
 #endif
@@ -389,8 +396,13 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     if constexpr (kTail) {
         // register hand-over (see the warp-role table): the light warpgroups release first, the heavy ones then grow
-        if (warp >= kWarpMma) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        else                  asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+#ifndef CNNACC_REGS_WG5
+#define CNNACC_REGS_WG5 48
+#define CNNACC_REGS_WG6 48
+#endif
+        if (warp >= kWarpTail0)    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(CNNACC_REGS_WG6));
+        else if (warp >= kWarpMma) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(CNNACC_REGS_WG5));
+        else                       asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     }
 
     auto wait_or_flag = [&](uint32_t b, uint32_t parity, int code) {
@@ -398,6 +410,10 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
         // ~4 s budget (a wait this long means a broken pipeline, not time-slicing or a debugger); once any wait has timed
         // out every later wait gives up quickly so the CTA drains.  A reported timeout invalidates the whole launch.
         if (!mbar_wait(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : kWaitBudgetClk)) atomicOr(s_err, code);
+    };
+    auto wait_or_flag_l0 = [&](uint32_t b, uint32_t parity, int code) {      // the same with a short sleep between polls
+        if (mbar_try(b, parity)) return;
+        if (!mbar_wait<CNNACC_L0_WAIT_SLEEP_NS>(b, parity, *reinterpret_cast<volatile int*>(s_err) ? 2000LL : kWaitBudgetClk)) atomicOr(s_err, code);
     };
 
     // TMA load of unit u (an image, or a window of a larger image) into an input slot; the box starts one pixel row above
@@ -445,11 +461,11 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 // lockstep behind the slowest), so only the kTail instantiation uses it.
                 constexpr bool kRendezvous = kTail && CNNACC_L0_RENDEZVOUS;
                 if (k > 0 && yp == warp) {
-                    if (!kRendezvous || warp == 0) wait_or_flag(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if (!kRendezvous || warp == 0) wait_or_flag_l0(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
                     if constexpr (kRendezvous) l0_bar_sync(kNamedL0Top);
                 }
                 if (k > 0 && yp >= 31 && yp - kL0Warps < 31) {
-                    if (!kRendezvous || warp == 0) wait_or_flag(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if (!kRendezvous || warp == 0) wait_or_flag_l0(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
                     if constexpr (kRendezvous) l0_bar_sync(kNamedL0Bot);
                 }
                 if (warp == 0) TRACE(2, 1); else if (warp == kL0Warps - 1) TRACE(3, 1);

@@ -1,5 +1,6 @@
 """Parity of the CUDA conv stack with the oracle, through the C ABI.  Bit-exact (integer path)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -330,4 +331,55 @@ def test_torch_call_is_ordered_on_the_current_stream(fc, port, shipped_weights):
                 assert np.array_equal(cls_f.cpu().numpy(), want)
     with pytest.raises(ValueError):
         a.run_batch(torch.zeros((2, 128, 128), dtype=torch.uint8, device="cuda"), out=torch.zeros(5, dtype=torch.uint8, device="cuda"))
+    a.close()
+
+
+def test_direct_path_at_the_largest_size(fc, port, shipped_weights):
+    """8192 x 8192 is the largest size the API accepts: layer 0 of the per-layer path has 256 x 256 = 65 536 tiles, one more
+    than gridDim.y allows (the tile index now shares gridDim.x with the image index).  Per-layer kernels == window mode on
+    the whole image, and the top-left corner == the oracle on a crop (outputs 0..13 only see pixels 0..119)."""
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    img = inputs.make_images(("rng", 55), 1, 8192, 8192)
+    direct = a.run_batch(img, direct=True)
+    assert direct.shape == (1, 64, 1024, 1024)
+    assert np.array_equal(direct, a.run_batch(img))
+    corner = oracle.port_infer_batch(port, np.ascontiguousarray(img[:, :128, :128]), shipped_weights, (7, 10, 11)).reshape(64, 16, 16)
+    assert np.array_equal(direct[0, :, :14, :14], corner[:, :14, :14])
+    a.close()
+
+
+def test_predictions_into_a_shared_registered_mapping(fc, port, shipped_weights, tmp_path):
+    """bench.py's stream_1m pattern: a file mapping page-locked with cnnacc_register_host receives the predictions of
+    device-resident chunks by plain async copies; they equal the host-pointer call's."""
+    import torch
+    n = 3000
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    a.load_classifier(*inputs.make_fc())
+    imgs = inputs.make_images(("rng", 56), n)
+    want_cls, want_probs, want_box = a.infer_batch(imgs)
+    path = "/dev/shm/cnnacc_test_%d.bin" % os.getpid()
+    with open(path, "wb") as f:
+        f.truncate(n * 44)
+    try:
+        shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(n * 44,))
+        unregister = fc.register_host(shm)
+        h_cls = torch.from_numpy(shm[:n * 4].view(np.int32))
+        h_probs = torch.from_numpy(shm[n * 4:n * 28].view(np.float32).reshape(n, 6))
+        h_box = torch.from_numpy(shm[n * 28:].view(np.int32).reshape(n, 4))
+        t = torch.from_numpy(imgs).cuda()
+        for c0 in range(0, n, 1024):
+            cls, probs, box = a.infer_batch(t[c0:c0 + 1024])
+            h_cls[c0:c0 + 1024].copy_(cls, non_blocking=True)
+            h_probs[c0:c0 + 1024].copy_(probs, non_blocking=True)
+            h_box[c0:c0 + 1024].copy_(box, non_blocking=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(h_cls.numpy(), want_cls) and np.array_equal(h_probs.numpy(), want_probs) and np.array_equal(h_box.numpy(), want_box)
+        unregister()
+        del h_cls, h_probs, h_box, shm
+    finally:
+        os.unlink(path)
     a.close()
