@@ -131,7 +131,9 @@ constexpr int kL0Dp4aWarps = CNNACC_L0_DP4A_WARPS;
 constexpr int kL0Warps = CNNACC_L0_WARPS, kEpiWarps = CNNACC_EPI_WARPS;   // multiples of 4 (TMEM lane quarter == warp % 4)
 static_assert(kL0Warps % 4 == 0 && kL0Warps <= 24 && (kEpiWarps == 4 || kEpiWarps == 8), "warp split");
 constexpr int kWarpMma = kL0Warps + kEpiWarps;       // the last warp: MMA issue and TMA loads
-constexpr int kFusedThreads = (kWarpMma + 1) * 32;    // 21 warps = 672
+// 4 epilogue warps: 21 warps at 80 registers.  8 epilogue warps (experiment, CNNACC_EPI_WARPS=8): 25 working warps only fit
+// with the setmaxnreg hand-over, so the grid is padded to 28 warps (warpgroup 6 = MMA warp + three idle ones).
+constexpr int kFusedThreads = (kEpiWarps == 8 ? 28 : kWarpMma + 1) * 32;    // 21 warps = 672
 constexpr int kTailWarps = kTailThreads / 32;         // 4 tail warps = warpgroup 6 of the kTail instantiation
 constexpr int kWarpTail0 = 24;                        // first tail warp (warpgroup aligned: setmaxnreg acts on warpgroups)
 constexpr int kTailKernelThreads = (kWarpTail0 + kTailWarps) * 32;   // 896
@@ -394,6 +396,15 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+#ifndef CNNACC_REGS_EPI8
+#define CNNACC_REGS_EPI8 80
+#define CNNACC_REGS_MMA8 24
+#endif
+    if constexpr (!kTail && kEpiWarps == 8) {
+        if (warp >= kWarpMma)      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(CNNACC_REGS_MMA8));
+        else if (warp >= kL0Warps) { if (CNNACC_REGS_EPI8 > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(CNNACC_REGS_EPI8)); }
+        else                       asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    }
     if constexpr (kTail) {
         // register hand-over (see the warp-role table): the light warpgroups release first, the heavy ones then grow
 #ifndef CNNACC_REGS_WG5
@@ -1021,6 +1032,7 @@ inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const C
     P.done_flag = (n == 1 && !win && !tail) ? done_flag : nullptr;
     P.done_seq = done_seq;
     if (win && tail) return (int)cudaErrorInvalidValue;
+    if (tail && kEpiWarps != 4) return (int)cudaErrorNotSupported;       // the tail's warp layout assumes 4 epilogue warps
     if (!tail && !d_feats) return (int)cudaErrorInvalidValue;
     std::memset(&P.tail, 0, sizeof(P.tail));
     if (tail) P.tail = *tail;
