@@ -2,6 +2,7 @@
 #include "../../include/cnnacc.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +37,7 @@ struct Slot {
 };
 
 std::string g_create_error;
+std::atomic<int64_t> g_pdl_seq{0};              // programmatic conv-stack launches of ALL handles (see conv_stack_device)
 
 }  // namespace
 
@@ -81,6 +83,14 @@ struct cnnacc_handle {
     uint8_t *d_img1 = nullptr, *d_bram = nullptr;
     bool image_loaded = false, started = false;
     int64_t launches = 0;
+    // Programmatic dependent launch of back-to-back conv-stack launches (conv_stack_device): the address ranges of the
+    // launches since the last one that waited for its predecessor.  A new launch may skip the wait only when it directly
+    // follows the newest of them on the same stream and neither reads nor writes anything they write, nor writes what they read.
+    struct PdlRecord { const uint8_t *in_lo, *in_hi, *out_lo, *out_hi; };
+    PdlRecord pdl_hist[16];
+    int pdl_n = 0;
+    int64_t pdl_launch_id = -1, pdl_global_seq = -1;
+    cudaStream_t pdl_stream = nullptr;
     std::string err;
 };
 
@@ -134,10 +144,37 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
                       uint8_t* d_feats, uint32_t flags, uint8_t* d_l0, uint8_t* d_l1) {
     const bool fused_ok = (H == CNNACC_IMG && W == CNNACC_IMG) && !(flags & CNNACC_FLAG_DIRECT) && h->fused.ready;
     if (fused_ok) {
+        // May this launch overlap the previous conv-stack launch (no griddepcontrol.wait)?  Only if that one is the last thing
+        // this handle launched, on the same stream, and none of the launches since the last full wait shares memory with it.
+        static const bool pdl_on = [] { const char* e = getenv("CNNACC_PDL"); return !(e && e[0] == '0'); }();
+        // Why a waiting launch is enough of a fence: every launch in such a chain fills all SMs with one CTA each, so a CTA of
+        // launch B only starts on an SM after the CTAs of A, A-1, ... there have exited -- "A complete" implies the whole chain
+        // is.  Launches smaller than the SM count therefore always wait and break the chain, and so does any other kernel of
+        // this handle (launch counter) or a conv-stack launch of ANOTHER handle (global sequence number).
+        int pdl_wait = -1;                               // -1: plain launch
+        if (pdl_on && !(flags & CNNACC_FLAG_KEEP_MAPS)) {
+            const cnnacc_handle::PdlRecord r = {d_imgs, d_imgs + (size_t)n * CNNACC_FEAT_BYTES, d_feats, d_feats + (size_t)n * CNNACC_FEAT_BYTES};
+            auto overlap = [](const uint8_t* a0, const uint8_t* a1, const uint8_t* b0, const uint8_t* b1) { return a0 < b1 && b0 < a1; };
+            bool indep = n >= h->sm_count && h->pdl_n > 0 && h->pdl_n < 16 && h->pdl_launch_id == h->launches && h->pdl_stream == stream &&
+                         h->pdl_global_seq == g_pdl_seq.load();
+            for (int i = 0; indep && i < h->pdl_n; i++) {
+                const auto& p = h->pdl_hist[i];
+                indep = !overlap(r.in_lo, r.in_hi, p.out_lo, p.out_hi) && !overlap(r.out_lo, r.out_hi, p.out_lo, p.out_hi) &&
+                        !overlap(r.out_lo, r.out_hi, p.in_lo, p.in_hi);
+            }
+            pdl_wait = indep ? 0 : 1;
+            if (!indep) h->pdl_n = 0;                    // this launch waits: everything before it is complete when it runs
+            if (n >= h->sm_count) h->pdl_hist[h->pdl_n++] = r;
+            h->pdl_stream = stream;
+            h->pdl_global_seq = ++g_pdl_seq;
+        } else {
+            h->pdl_n = 0;
+        }
         int rc = launch_fused(h->fused, stream, d_imgs, n, d_feats, h->shifts, h->sm_count,
                               (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l0 : nullptr,
-                              (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l1 : nullptr);
+                              (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l1 : nullptr, nullptr, pdl_wait);
         h->launches++;
+        h->pdl_launch_id = h->launches;
         if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
         return 0;
     }

@@ -175,6 +175,8 @@ struct FusedParams {
     uint8_t* dump_l1;            // optional [n][32][32][32]
     int* status;                 // device int, OR-ed error bits
     int* status_host;            // the same in mapped pinned host memory: polled without a CUDA call
+    int pdl_wait;                // conv-only instantiation, launched with programmatic stream serialisation: 1 = execute
+                                 // griddepcontrol.wait before touching global memory (the launch may depend on the previous one)
     int* done_flag;              // optional (single-CTA latency path): mapped pinned host word that receives done_seq once the
     int done_seq;                // last feature store has landed, so the host can spin on it instead of a stream synchronise
     // window mode (images larger than 128x128, tiling.cuh): unit u = window (u % win_ntx, (u / win_ntx) % win_nty) of image
@@ -396,6 +398,14 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    if constexpr (!kWin && !kTail) {
+        // Programmatic dependent launch (launch_fused_map): the NEXT conv-stack launch of this stream may be scheduled as soon
+        // as every CTA of this one has got here, so its CTAs start on each SM the moment this grid's CTA there exits -- no
+        // launch gap, and SMs that got one image fewer do not idle until the slowest is done.  This grid in turn must not
+        // touch global memory before its predecessor has completed, unless the host has shown the two to be independent.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (P.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 #ifndef CNNACC_REGS_EPI8
 #define CNNACC_REGS_EPI8 80
 #define CNNACC_REGS_MMA8 24
@@ -1027,8 +1037,9 @@ struct FusedWindows {             // window mode: see FusedParams
 };
 inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const CUtensorMap& map, int64_t n, uint8_t* d_feats,
                             const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const FusedWindows* win = nullptr,
-                            const TailArgs* tail = nullptr, int* done_flag = nullptr, int done_seq = 0) {
+                            const TailArgs* tail = nullptr, int* done_flag = nullptr, int done_seq = 0, int pdl_wait = -1) {
     FusedParams P;
+    P.pdl_wait = pdl_wait != 0;
     P.done_flag = (n == 1 && !win && !tail) ? done_flag : nullptr;
     P.done_seq = done_seq;
     if (win && tail) return (int)cudaErrorInvalidValue;
@@ -1054,18 +1065,30 @@ inline int launch_fused_map(const FusedWeights& fw, cudaStream_t stream, const C
     const int grid = (int)std::min<int64_t>(n, sm_count);
     if (win)       conv_stack_fused_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
     else if (tail) conv_stack_fused_kernel<false, true><<<grid, kTailKernelThreads, kFusedSmem, stream>>>(map, P);
-    else           conv_stack_fused_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    else if (pdl_wait < 0) conv_stack_fused_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, stream>>>(map, P);
+    else {
+        // programmatic stream serialisation: this launch may begin while the previous kernel of the stream is still
+        // running; pdl_wait (above) says whether the kernel must then wait for it before its first global access
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = kFusedSmem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, conv_stack_fused_kernel<false, false>, map, P);
+    }
     return (int)cudaGetLastError();
 }
 
 // One launch for n device-resident images.
 inline int launch_fused(const FusedWeights& fw, cudaStream_t stream, const uint8_t* d_imgs, int64_t n, uint8_t* d_feats,
-                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const TailArgs* tail = nullptr) {
+                        const int* shifts, int sm_count, uint8_t* dump_l0, uint8_t* dump_l1, const TailArgs* tail = nullptr,
+                        int pdl_wait = -1) {
     if (n <= 0) return 0;
     CUtensorMap map;
     int rc = fused_encode_map(d_imgs, n, &map);
     if (rc) return rc;
-    return launch_fused_map(fw, stream, map, n, d_feats, shifts, sm_count, dump_l0, dump_l1, nullptr, tail);
+    return launch_fused_map(fw, stream, map, n, d_feats, shifts, sm_count, dump_l0, dump_l1, nullptr, tail, nullptr, 0, pdl_wait);
 }
 
 // Reads (and clears) the status word; non-zero = a pipeline wait timed out inside some launch.  The caller has

@@ -383,3 +383,58 @@ def test_predictions_into_a_shared_registered_mapping(fc, port, shipped_weights,
     finally:
         os.unlink(path)
     a.close()
+
+
+def test_back_to_back_launches_with_and_without_dependencies(fc, port, shipped_weights):
+    """Consecutive device-pointer run_batch calls are launched with programmatic stream serialisation and skip the wait for
+    their predecessor only when the host can show them independent.  Dependent patterns must still be ordered: the same output
+    buffer written twice (last writer wins), an output buffer that aliases the previous input, many rotating buffers, small
+    grids in between, and two handles sharing a stream."""
+    import torch
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    st = torch.cuda.Stream()
+    a.use_stream(st.cuda_stream)
+    n = 1500
+    host = [inputs.make_images(("rng", 700 + i), n) for i in range(4)]
+    want = [oracle.port_infer_batch(port, im, shipped_weights, (7, 10, 11)).reshape(n, 64, 16, 16) for im in host]
+    with torch.cuda.stream(st):
+        x = [torch.from_numpy(im).cuda() for im in host]
+        outs = [torch.empty((n, 64, 16, 16), dtype=torch.uint8, device="cuda") for _ in range(4)]
+        shared = torch.empty((n, 64, 16, 16), dtype=torch.uint8, device="cuda")
+        for rep in range(20):
+            for i in range(4):                       # independent: rotating inputs and outputs
+                a.run_batch(x[i], out=outs[i])
+            for i in range(4):                       # WAW: one output buffer, last writer must win
+                a.run_batch(x[i], out=shared)
+            a.run_batch(x[0][:7], out=outs[0][:7])   # a small grid in the chain
+            a.run_batch(x[1], out=outs[1])
+        st.synchronize()
+        for i in range(4):
+            assert np.array_equal(outs[i].cpu().numpy(), want[i]), i
+        assert np.array_equal(shared.cpu().numpy(), want[3])
+        # RAW through an aliased buffer: the second launch reads what the first wrote (features reinterpreted as images)
+        chain_in = torch.from_numpy(host[0][:148 * 4]).cuda()
+        mid = torch.empty((148 * 4, 64, 16, 16), dtype=torch.uint8, device="cuda")
+        for rep in range(10):
+            a.run_batch(chain_in, out=mid)
+            second = a.run_batch(mid.view(148 * 4, 128, 128))
+        st.synchronize()
+        mid_h = mid.cpu().numpy()
+        assert np.array_equal(mid_h, want[0][:148 * 4])
+        want2 = oracle.port_infer_batch(port, mid_h.reshape(148 * 4, 128, 128), shipped_weights, (7, 10, 11)).reshape(-1, 64, 16, 16)
+        assert np.array_equal(second.cpu().numpy(), want2)
+        # two handles on one stream: the second handle's launch reads the first handle's output
+        b = fc.CNNAccelerator()
+        b.load_weights(shipped_weights)
+        b.set_shifts(7, 10, 11)
+        b.use_stream(st.cuda_stream)
+        for rep in range(10):
+            a.run_batch(chain_in, out=mid)
+            third = b.run_batch(mid.view(148 * 4, 128, 128))
+            a.run_batch(x[2], out=outs[2])
+        st.synchronize()
+        assert np.array_equal(third.cpu().numpy(), want2) and np.array_equal(outs[2].cpu().numpy(), want[2])
+        b.close()
+    a.close()
