@@ -296,10 +296,14 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 #define CNNACC_L0_WAIT_SLEEP_NS 0
 #endif
 #ifndef CNNACC_L0_RENDEZVOUS
-#define CNNACC_L0_RENDEZVOUS 1
+#define CNNACC_L0_RENDEZVOUS 4     // kTail instantiation: sixteen layer-0 warps behind one poller at the A1BotFree point only
 #endif
 constexpr int kNamedL0Top = 8, kNamedL0Bot = 9;       // the sixteen layer-0 warps behind one poller (see the layer-0 loop)
 __device__ __forceinline__ void l0_bar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kL0Warps * 32) : "memory"); }
+__device__ __forceinline__ void l0_group_bar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kL0Warps * 8) : "memory"); }
+#ifndef CNNACC_L0_RENDEZVOUS_CONV
+#define CNNACC_L0_RENDEZVOUS_CONV 0
+#endif
 constexpr int kNamedStageFull = 3, kNamedStageFree = 4;
 // ... and the same between the tail's front warps (24-27) and back warps (22-23) for the 1 KiB CAM buffer; 2 and 5 are the
 // front's and the back's own barriers.
@@ -477,17 +481,25 @@ conv_stack_fused_kernel(const __grid_constant__ CUtensorMap in_map, const __grid
                 // slots while they wait.  (ncu, profiles/r2a_conv_*: sixteen warps polling A1TopFree executed 2 166 try_waits
                 // per image -- four pollers per sub-partition next to the one epilogue warp whose progress they wait for.)
                 // Every layer-0 warp reaches each of the two points exactly once per image, so the barriers stay in step.
-                // Measured (tools/pipe_timing_short.py): with the tail warps competing for issue slots the rendezvous is worth
-                // +2.7 % (15.67 -> 16.09 M img/s); without them it costs 9 % (19.73 -> 17.88: the sixteen warps then move in
-                // lockstep behind the slowest), so only the kTail instantiation uses it.
-                constexpr bool kRendezvous = kTail && CNNACC_L0_RENDEZVOUS;
+                // Measured (tools/pipe_timing_short.py, M img/s conv-only / infer_batch when BOTH instantiations use the mode):
+                // none 19.73 / 15.67, both points 17.88 / 16.09, per sub-partition groups 18.82 / 15.62, top point only
+                // 19.29 / 16.02, bottom point only 19.08 / 16.23.  Without the tail warps any rendezvous costs throughput (the
+                // warps then move in lockstep behind the slowest); with them the bottom-only one is worth +3.5 %.  So the
+                // conv-only instantiation uses none and the kTail instantiation mode 4.
+                // CNNACC_L0_RENDEZVOUS: 0 none, 1 all sixteen warps behind warp 0 (both points), 2 per sub-partition group of four
+                // (warps s, s+4, s+8, s+12 behind warp s), 3 = 1 for the top point only, 4 = 1 for the bottom point only
+                constexpr int kRv = kTail ? CNNACC_L0_RENDEZVOUS : CNNACC_L0_RENDEZVOUS_CONV;
                 if (k > 0 && yp == warp) {
-                    if (!kRendezvous || warp == 0) wait_or_flag_l0(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                    if constexpr (kRendezvous) l0_bar_sync(kNamedL0Top);
+                    const bool rv = kRv == 1 || kRv == 2 || kRv == 3;
+                    const bool poller = !rv || (kRv == 2 ? warp < 4 : warp == 0);
+                    if (poller) wait_or_flag_l0(bar(kBarA1TopFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if (rv) { if (kRv == 2) l0_group_bar_sync(8 + (warp & 3)); else l0_bar_sync(kNamedL0Top); }
                 }
                 if (k > 0 && yp >= 31 && yp - kL0Warps < 31) {
-                    if (!kRendezvous || warp == 0) wait_or_flag_l0(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
-                    if constexpr (kRendezvous) l0_bar_sync(kNamedL0Bot);
+                    const bool rv = kRv == 1 || kRv == 2 || kRv == 4;
+                    const bool poller = !rv || (kRv == 2 ? warp < 4 : warp == 0);
+                    if (poller) wait_or_flag_l0(bar(kBarA1BotFree), (uint32_t)(k - 1) & 1, kErrAct1Timeout);
+                    if (rv) { if (kRv == 2) l0_group_bar_sync(12 + (warp & 3)); else l0_bar_sync(kNamedL0Bot); }
                 }
                 if (warp == 0) TRACE(2, 1); else if (warp == kL0Warps - 1) TRACE(3, 1);
                 if (use_dp4a) {
