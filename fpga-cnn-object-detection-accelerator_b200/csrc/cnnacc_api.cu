@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@
 #include "cam_upsampled.cuh"
 #include "preprocess.cuh"
 #include "pil_resize.cuh"
+#include "pdl_chain.h"
 #include "tiling.cuh"
 #include "weights_pack.h"
 
@@ -83,14 +85,7 @@ struct cnnacc_handle {
     uint8_t *d_img1 = nullptr, *d_bram = nullptr;
     bool image_loaded = false, started = false;
     int64_t launches = 0;
-    // Programmatic dependent launch of back-to-back conv-stack launches (conv_stack_device): the address ranges of the
-    // launches since the last one that waited for its predecessor.  A new launch may skip the wait only when it directly
-    // follows the newest of them on the same stream and neither reads nor writes anything they write, nor writes what they read.
-    struct PdlRecord { const uint8_t *in_lo, *in_hi, *out_lo, *out_hi; };
-    PdlRecord pdl_hist[16];
-    int pdl_n = 0;
-    int64_t pdl_launch_id = -1, pdl_global_seq = -1;
-    cudaStream_t pdl_stream = nullptr;
+    PdlChain pdl;                                   // overlapped back-to-back conv-stack launches (pdl_chain.h)
     std::string err;
 };
 
@@ -153,28 +148,17 @@ int conv_stack_device(cnnacc_handle* h, cudaStream_t stream, const uint8_t* d_im
         // this handle (launch counter) or a conv-stack launch of ANOTHER handle (global sequence number).
         int pdl_wait = -1;                               // -1: plain launch
         if (pdl_on && !(flags & CNNACC_FLAG_KEEP_MAPS)) {
-            const cnnacc_handle::PdlRecord r = {d_imgs, d_imgs + (size_t)n * CNNACC_FEAT_BYTES, d_feats, d_feats + (size_t)n * CNNACC_FEAT_BYTES};
-            auto overlap = [](const uint8_t* a0, const uint8_t* a1, const uint8_t* b0, const uint8_t* b1) { return a0 < b1 && b0 < a1; };
-            bool indep = n >= h->sm_count && h->pdl_n > 0 && h->pdl_n < 16 && h->pdl_launch_id == h->launches && h->pdl_stream == stream &&
-                         h->pdl_global_seq == g_pdl_seq.load();
-            for (int i = 0; indep && i < h->pdl_n; i++) {
-                const auto& p = h->pdl_hist[i];
-                indep = !overlap(r.in_lo, r.in_hi, p.out_lo, p.out_hi) && !overlap(r.out_lo, r.out_hi, p.out_lo, p.out_hi) &&
-                        !overlap(r.out_lo, r.out_hi, p.in_lo, p.in_hi);
-            }
-            pdl_wait = indep ? 0 : 1;
-            if (!indep) h->pdl_n = 0;                    // this launch waits: everything before it is complete when it runs
-            if (n >= h->sm_count) h->pdl_hist[h->pdl_n++] = r;
-            h->pdl_stream = stream;
-            h->pdl_global_seq = ++g_pdl_seq;
+            const uintptr_t in = reinterpret_cast<uintptr_t>(d_imgs), out = reinterpret_cast<uintptr_t>(d_feats);
+            const PdlRange r = {in, in + (size_t)n * CNNACC_FEAT_BYTES, out, out + (size_t)n * CNNACC_FEAT_BYTES};
+            const int64_t seq_now = g_pdl_seq.load(), seq_mine = ++g_pdl_seq;
+            pdl_wait = h->pdl.decide(r, n, h->sm_count, reinterpret_cast<uintptr_t>(stream), h->launches, seq_now, seq_mine);
         } else {
-            h->pdl_n = 0;
+            h->pdl.reset();
         }
         int rc = launch_fused(h->fused, stream, d_imgs, n, d_feats, h->shifts, h->sm_count,
                               (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l0 : nullptr,
                               (flags & CNNACC_FLAG_KEEP_MAPS) ? d_l1 : nullptr, nullptr, pdl_wait);
         h->launches++;
-        h->pdl_launch_id = h->launches;
         if (rc != 0) return fail(h, CNNACC_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
         return 0;
     }
@@ -477,6 +461,22 @@ int cnnacc_pack_weights_host(const uint8_t* weights_bin, size_t n, uint32_t* w0,
     return CNNACC_OK;
 }
 
+int cnnacc_pdl_chain_host(int n_launches, const uint64_t* ranges, const int64_t* n_images, const int32_t* stream_id,
+                          const int32_t* foreign_before, int sm_count, int32_t* wait_out) {
+    if (n_launches < 0 || !ranges || !n_images || !stream_id || !foreign_before || !wait_out || sm_count < 1) return CNNACC_ERR_ARG;
+    PdlChain chain;
+    int64_t launches = 0, seq = 0;
+    for (int i = 0; i < n_launches; i++) {
+        if (foreign_before[i] & 1) launches++;          // another kernel of the same handle in between
+        if (foreign_before[i] & 2) seq++;               // a conv-stack launch of another handle in between
+        const PdlRange r = {(uintptr_t)ranges[4 * i], (uintptr_t)ranges[4 * i + 1], (uintptr_t)ranges[4 * i + 2], (uintptr_t)ranges[4 * i + 3]};
+        const int64_t seq_now = seq, seq_mine = ++seq;
+        wait_out[i] = chain.decide(r, n_images[i], sm_count, (uintptr_t)stream_id[i], launches, seq_now, seq_mine);
+        launches++;
+    }
+    return CNNACC_OK;
+}
+
 int cnnacc_tile_plan_host(int n_out, int* origin, int* first, int* end, int cap) {
     if (n_out < 16 || n_out > 1024 || !origin || !first || !end) return CNNACC_ERR_ARG;
     const TilePlan p = make_tile_plan(n_out);
@@ -693,6 +693,10 @@ int cnnacc_infer_one(cnnacc_handle* h, const uint8_t* img, uint8_t* feat, float*
 int cnnacc_load_classifier(cnnacc_handle* h, const float* fc_w, const float* fc_b, int n_cls) {
     if (!h || !fc_w || !fc_b) return fail(h, CNNACC_ERR_ARG, "NULL argument");
     if (n_cls < 1 || n_cls > kMaxClasses) return fail(h, CNNACC_ERR_ARG, "n_cls outside 1..16");
+    // The CAM forms w * float(byte) as fma(w, 2^23 + byte, -w * 2^23) (tail.cuh), which is exact as long as w * 2^23 is finite;
+    // weights beyond 2^100 (or not finite) make every logit meaningless anyway and are rejected here.
+    for (size_t i = 0; i < (size_t)n_cls * 1024; i++)
+        if (!(std::fabs(fc_w[i]) < 1.2676506002282294e30f)) return fail(h, CNNACC_ERR_ARG, "classifier weight not finite or |w| >= 2^100");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());
     if (!h->d_fcw) CU(h, cudaMalloc(&h->d_fcw, (size_t)kMaxClasses * 1024 * sizeof(float)));

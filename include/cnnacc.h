@@ -92,6 +92,14 @@ int cnnacc_get_accumulator_bits(const cnnacc_handle *h);
 #define CNNACC_PACK_B2_BYTES 18432
 int cnnacc_pack_weights_host(const uint8_t *weights_bin, size_t n, uint32_t *w0, uint8_t *b1, uint8_t *b2);
 
+/* Host-only replay of the bookkeeping behind the overlapped conv-stack launches (csrc/pdl_chain.h): for
+ * a sequence of device-pointer cnnacc_run_batch launches i -- ranges[4i..4i+3] = input begin / end, output begin / end
+ * addresses, n_images[i], stream_id[i], foreign_before[i] bit 0 = another kernel of the handle was launched in between, bit 1 =
+ * another handle launched a conv stack in between -- wait_out[i] = 1 when launch i must wait for its predecessor before touching
+ * memory, 0 when it may overlap it.  No GPU needed; tests/ check the dependency rules with it. */
+int cnnacc_pdl_chain_host(int n_launches, const uint64_t *ranges, const int64_t *n_images, const int32_t *stream_id,
+                          const int32_t *foreign_before, int sm_count, int32_t *wait_out);
+
 /* Host-only view of the window plan used for images larger than 128x128 (csrc/tiling.cuh): along one dimension with
  * n_out = size/8 outputs, window i starts at output origin[i] (pixel 8*origin[i]) and owns outputs [first[i], end[i]).
  * Returns the number of windows (<= cap) or a negative code.  The FPGA's analogue is the 4-tile drain of layer 0
@@ -130,6 +138,7 @@ int cnnacc_infer_one(cnnacc_handle *h, const uint8_t *img, uint8_t *feat, float 
 
 /* ---- follow-on kernels: spatial-bin pool + linear + softmax + CAM bbox ---------------------
  * load_classifier: fc_w [n_cls][1024] f32 row-major, fc_b [n_cls] (realtime_detect.py:533-545), n_cls <= 16.
+ *                  Weights must be finite with |w| < 2^100 (else -2).
  * classify_batch : classify_vec + bbox_vec (realtime_detect.py:68-116) on feats [n][64][256] u8.
  *                  probs [n][n_cls] f32, cls [n] i32, bbox [n][4] i32 (x1,y1,x2,y2); any output may be NULL.
  * infer_batch    : run_batch (128x128) followed by classify_batch without the features leaving the GPU. */

@@ -81,3 +81,50 @@ def test_window_plan_for_large_images(lib):
                 owned[o] += 1
         assert (owned == 1).all()
     assert lib.cnnacc_tile_plan_host(8, p(buf()), p(buf()), p(buf()), 80) == fc._lib.ERR_ARG
+
+
+def _pdl(launches, sm_count=148):
+    """launches: list of (in_lo, in_hi, out_lo, out_hi, n_images, stream, foreign) -> list of wait decisions."""
+    import ctypes
+    lib = fc.load()
+    n = len(launches)
+    ranges = np.array([v for l in launches for v in l[:4]], dtype=np.uint64)
+    n_img = np.array([l[4] for l in launches], dtype=np.int64)
+    stream = np.array([l[5] for l in launches], dtype=np.int32)
+    foreign = np.array([l[6] for l in launches], dtype=np.int32)
+    out = np.full(n, -1, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.cnnacc_pdl_chain_host(n, p(ranges), p(n_img), p(stream), p(foreign), sm_count, p(out)) == 0
+    return out.tolist()
+
+
+def test_overlapped_launch_bookkeeping():
+    """The rules behind `griddepcontrol.wait` being skipped (csrc/pdl_chain.h): a launch may overlap its predecessor only if
+    it follows it directly on the same stream, fills the GPU, and shares no memory (RAW, WAW, WAR) with any launch since the
+    last one that waited."""
+    K = 16384
+    buf = lambda i, n=4096: (0x1000_0000 + i * 0x1000_0000, 0x1000_0000 + i * 0x1000_0000 + n * K)
+    L = lambda i_in, i_out, n=4096, stream=7, foreign=0: (*buf(i_in, n), *buf(i_out, n), n, stream, foreign)
+    # 1. rotating independent buffers: the first launch waits, the rest overlap, a full chain (16) forces a wait
+    seq = [L(2 * i, 2 * i + 1) for i in range(20)]
+    w = _pdl(seq)
+    assert w[0] == 1 and w[1:16] == [0] * 15 and w[16] == 1 and w[17:] == [0] * 3
+    # 2. WAW: same output buffer twice -> wait
+    assert _pdl([L(0, 1), L(2, 1)]) == [1, 1]
+    # 3. RAW: reads what the previous launch wrote -> wait; also against an OLDER member of the chain
+    assert _pdl([L(0, 1), L(1, 2)]) == [1, 1]
+    assert _pdl([L(0, 1), L(2, 3), L(1, 4)]) == [1, 0, 1]
+    # 4. WAR: writes what a chain member still reads -> wait
+    assert _pdl([L(0, 1), L(2, 0)]) == [1, 1]
+    # 5. partial overlap of ranges counts
+    a = (0x1000, 0x1000 + 4096 * K, 0x9000_0000, 0x9000_0000 + 4096 * K, 4096, 7, 0)
+    b = (0x5000_0000, 0x5000_0000 + 4096 * K, 0x9000_0000 + 4096 * K - 1, 0x9000_0000 + 2 * 4096 * K, 4096, 7, 0)
+    assert _pdl([a, b]) == [1, 1]
+    # 6. a grid smaller than the SM count always waits and is no fence: its successor waits too
+    assert _pdl([L(0, 1), L(2, 3), L(4, 5, n=100), L(6, 7), L(8, 9)]) == [1, 0, 1, 1, 0]
+    # 7. another kernel of the handle, another handle's conv launch, or another stream in between -> wait
+    assert _pdl([L(0, 1), L(2, 3, foreign=1), L(4, 5)]) == [1, 1, 0]
+    assert _pdl([L(0, 1), L(2, 3, foreign=2), L(4, 5)]) == [1, 1, 0]
+    assert _pdl([L(0, 1), L(2, 3, stream=8), L(4, 5, stream=8)]) == [1, 1, 0]
+    # 8. after a waiting launch only the launches since then matter: buffer 1 is free to be reused
+    assert _pdl([L(0, 1), L(2, 3), L(4, 3), L(6, 1)]) == [1, 0, 1, 0]

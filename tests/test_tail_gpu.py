@@ -315,3 +315,17 @@ def test_fused_tail_many_classes_and_saturated_maps(shipped_weights):
             assert c == cls[i] and np.abs(p - probs[i]).max() <= PROB_ATOL, (n_cls, shifts, i)
             assert tuple(box[i]) == np_oracle.bbox_vec(feats[i], c, w)[0], (n_cls, shifts, i)
     a.close()
+
+
+def test_classifier_weight_domain(acc):
+    """Weights must be finite and below 2^100 (the CAM's one-FMA product is exact only while w * 2^23 is finite)."""
+    w, b = inputs.make_fc()
+    for bad in (np.inf, np.nan, 2.0 ** 100, -1e31):
+        w2 = w.copy()
+        w2[3, 500] = bad
+        with pytest.raises(ValueError):
+            acc.load_classifier(w2, b)
+    w2 = w.copy()
+    w2[3, 500] = np.float32(2.0 ** 99)
+    acc.load_classifier(w2, b)                      # accepted
+    acc.load_classifier(w, b)
