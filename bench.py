@@ -367,6 +367,22 @@ class NvmlWindow:
                 "reasons": sorted(name for name, bit in ClockSampler.REASONS if bits & bit)}
 
 
+def create_shared_predictions(path, n_images):
+    """Rank 0: the file behind the ONE host array every rank's GPU copies its predictions into."""
+    with open(path, "wb") as f:
+        f.truncate(n_images * PRED_BYTES)
+
+
+def map_shared_predictions(path, n_images):
+    """Every rank: map the file -> (raw bytes, cls [n] i32, probs [n,6] f32, bbox [n,4] i32), all views of one mapping laid out
+    array after array; a rank writes rows shard_range(n, rank, world) of each."""
+    shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(n_images * PRED_BYTES,))
+    cls = shm[:n_images * 4].view(np.int32)
+    probs = shm[n_images * 4:n_images * 28].view(np.float32).reshape(n_images, 6)
+    bbox = shm[n_images * 28:].view(np.int32).reshape(n_images, 4)
+    return shm, cls, probs, bbox
+
+
 def oracle_spot_check(images, cls, probs, bbox, weights, fc_w, fc_b):
     """Predictions of `images` (numpy [m,128,128]) against the oracle (conv stack: liboracle.so; classifier / box: the numpy
     restatement).  Returns (checked, mismatches)."""
@@ -399,15 +415,11 @@ def run_stream_1m(acc, fc, torch, ddist, rank, world, local, weights, gen):
     path = f"/dev/shm/cnnacc_stream_{tag}.bin"
     total = STREAM_IMAGES * PRED_BYTES
     if rank == 0:
-        with open(path, "wb") as f:
-            f.truncate(total)
+        create_shared_predictions(path, STREAM_IMAGES)
     if ddist is not None:
         ddist.barrier()
-    shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(total,))
+    shm, h_cls, h_probs, h_bbox = map_shared_predictions(path, STREAM_IMAGES)
     unregister = fc.register_host(shm)
-    h_cls = shm[:STREAM_IMAGES * 4].view(np.int32)
-    h_probs = shm[STREAM_IMAGES * 4:STREAM_IMAGES * 28].view(np.float32).reshape(STREAM_IMAGES, 6)
-    h_bbox = shm[STREAM_IMAGES * 28:].view(np.int32).reshape(STREAM_IMAGES, 4)
     t_cls, t_probs, t_bbox = (torch.from_numpy(a[lo:hi]) for a in (h_cls, h_probs, h_bbox))
     stream = torch.cuda.Stream(device=local)
     acc.use_stream(stream.cuda_stream)

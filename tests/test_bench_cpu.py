@@ -81,3 +81,53 @@ def test_roofline_traffic_comes_from_the_newest_committed_capture():
     assert 16384 <= per_image <= 40000            # one image in, (up to) one feature map out
     rounds = [int(f[1:f.index("_")]) for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_ncu_summary.txt") and f[1].isdigit()]
     assert name.startswith(f"r{max(rounds)}_") or per_image                        # newest round preferred
+
+
+def _shared_worker(rank, world, port, path, n, q):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if rank == 0:
+        bench.create_shared_predictions(path, n)
+    dist.barrier()
+    shm, cls, probs, bbox = bench.map_shared_predictions(path, n)
+    lo, hi = bench.shard_range(n, rank, world)
+    idx = np.arange(lo, hi)
+    cls[lo:hi] = idx % 6                                   # what this rank's GPU would copy into its slice
+    probs[lo:hi] = (idx[:, None] * 6 + np.arange(6)).astype(np.float32)
+    bbox[lo:hi] = idx[:, None] * 4 + np.arange(4)
+    shm.flush()
+    dist.barrier()
+    ok = None
+    if rank == 0:                                          # rank 0 holds the gathered result without a collective
+        all_idx = np.arange(n)
+        ok = bool(np.array_equal(cls, all_idx % 6) and np.array_equal(bbox, all_idx[:, None] * 4 + np.arange(4)) and
+                  np.array_equal(probs, (all_idx[:, None] * 6 + np.arange(6)).astype(np.float32)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_fill_one_shared_prediction_array():
+    """The gather of bench.py's stream_1m: every rank maps the same /dev/shm file and writes rows shard_range(...) of each
+    prediction array; rank 0 then reads the whole job's predictions.  (On the GPU box the writes are the GPUs' D2H copies.)"""
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    n = 100_001
+    path = f"/dev/shm/cnnacc_test_shared_{os.getpid()}.bin"
+    procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, path, n, q)) for r in range(2)]
+    try:
+        for p in procs:
+            p.start()
+        res = dict(q.get(timeout=120) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert res[0] is True and res[1] is None
+        assert os.path.getsize(path) == n * bench.PRED_BYTES
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
