@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "conv_direct.cuh"
 #include "conv_fused.cuh"
@@ -324,6 +325,19 @@ int check_fused_status(cnnacc_handle* h) {
     return 0;
 }
 
+// Host-pointer calls queue copies that read and write the CALLER's buffers.  If such a call returns early with an error the
+// queued work must not outlive it: the guard drains the ring's streams on every exit it was not dismissed on.
+struct RingDrain {
+    cnnacc_handle* h;
+    bool armed = true;
+    explicit RingDrain(cnnacc_handle* h_) : h(h_) {}
+    ~RingDrain() {
+        if (!armed) return;
+        for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) cudaStreamSynchronize(st);
+    }
+    int done(int rc) { armed = false; return rc; }       // normal exit: the call has synchronised already
+};
+
 int check_ready(cnnacc_handle* h) {
     if (!h) return CNNACC_ERR_ARG;
     if (!h->weights_loaded) return fail(h, CNNACC_ERR_STATE, "weights not loaded (call cnnacc_load_weights)");
@@ -347,7 +361,7 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     h->device = device_id;
     auto bail = [&](const char* what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
-        delete h;
+        cnnacc_destroy(h);                               // releases whatever was created so far (null members are skipped)
         return CNNACC_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail("cudaSetDevice", e);
@@ -356,7 +370,7 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
     if (prop.major != 10) {
         g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
                          "; this library is built for sm_100a (B200) only";
-        delete h;
+        cnnacc_destroy(h);
         return CNNACC_ERR_CUDA;
     }
     h->sm_count = prop.multiProcessorCount;
@@ -516,7 +530,8 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
     // chained by per-slot events, so copies in both directions and the kernels overlap.  (One stream per slot measured the
     // same or slightly worse; more than 4 slots made no difference: profiles/r1_e2e_chunk_sweep.txt.)
     CU(h, cudaStreamSynchronize(h->stream));
-    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));   // idle unless an earlier call failed midway
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));   // idle already (RingDrain)
+    RingDrain drain(h);
     // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
     // chunks; each chunk costs ~20-40 us of cross-engine hand-offs on top of its copies (tools/probe_pipeline.cu shows
     // the same for any H2D -> kernel -> D2H chain), so they should not be small either: a quarter of the call, clamped
@@ -557,7 +572,7 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
         CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));            // the last D2H is the last operation of the whole chain
-    return check_fused_status(h);
+    return drain.done(check_fused_status(h));
 }
 
 int cnnacc_load_image(cnnacc_handle* h, const uint8_t* img, size_t n) {
@@ -783,6 +798,7 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    RingDrain drain(h);
     if (n <= kSmallN) {                                      // latency path: one stream, one result copy
         Slot& s = h->slots[0];
         cudaStream_t st = h->st_k;
@@ -801,7 +817,7 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
         CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         small_pred_unpack(h, p, n, probs, cls, bbox, cls_given);
-        return src_is_images ? check_fused_status(h) : CNNACC_OK;
+        return drain.done(src_is_images ? check_fused_status(h) : CNNACC_OK);
     }
     // Same ring as cnnacc_run_batch's host path; only the predictions (44 B per image) come back, so the link carries
     // H2D traffic alone and the chunks can be a quarter of the call, clamped to 4..32 MiB.  The kernels write the
@@ -838,7 +854,7 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
         CU(h, cudaStreamSynchronize(h->st_k));
         small_pred_unpack(h, p, sn, probs ? probs + s0 * nc : nullptr, cls ? cls + s0 : nullptr, bbox ? bbox + s0 * 4 : nullptr, cls_given);
     }
-    return src_is_images ? check_fused_status(h) : CNNACC_OK;
+    return drain.done(src_is_images ? check_fused_status(h) : CNNACC_OK);
 }
 
 int cnnacc_classify_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, float* probs, int32_t* cls, int32_t* bbox, uint32_t flags) {
@@ -865,6 +881,7 @@ int cnnacc_pool_features(cnnacc_handle* h, const uint8_t* feats, int64_t n, floa
     }
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    RingDrain drain(h);
     const int64_t hchunk = std::min<int64_t>(n, 2048);
     int64_t ci = 0;
     for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
@@ -884,7 +901,7 @@ int cnnacc_pool_features(cnnacc_handle* h, const uint8_t* feats, int64_t n, floa
         CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
-    return CNNACC_OK;
+    return drain.done(CNNACC_OK);
 }
 
 int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, const int32_t* cls, int32_t* bbox, uint8_t* cam,
@@ -901,6 +918,7 @@ int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, con
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    RingDrain drain(h);
     const int64_t hchunk = std::min<int64_t>(n, 4096);
     int64_t ci = 0;
     for (int64_t i0 = 0; i0 < n; i0 += hchunk, ci++) {      // same ring as cnnacc_run_batch's host path
@@ -920,7 +938,7 @@ int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, con
         CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
-    return CNNACC_OK;
+    return drain.done(CNNACC_OK);
 }
 
 // shared body of preprocess_bgr (gray128 out) and detect_frames (predictions out)
@@ -966,6 +984,7 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
+    RingDrain drain(h);
     if (n <= kSmallN && n * frame_sz <= ((size_t)64 << 20)) {   // latency path: one stream, one result copy
         Slot& s = h->slots[0];
         cudaStream_t st = h->st_k;
@@ -978,7 +997,7 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
         if (detect) CU(h, cudaMemcpyAsync(h->h_pred_small, h->d_pred_small, p.bytes, cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         if (detect) small_pred_unpack(h, p, n, probs, cls, bbox, false);
-        return detect ? check_fused_status(h) : CNNACC_OK;
+        return drain.done(detect ? check_fused_status(h) : CNNACC_OK);
     }
     // frames are large (a VGA frame is 900 KiB): stage about 16 MiB of them per slot; predictions as in predict_impl
     const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, (int64_t)(((size_t)16 << 20) / frame_sz)));
@@ -1009,7 +1028,7 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
         }
     }
     CU(h, cudaStreamSynchronize(h->st_d2h));
-    return detect ? check_fused_status(h) : CNNACC_OK;
+    return drain.done(detect ? check_fused_status(h) : CNNACC_OK);
 }
 
 int cnnacc_preprocess_bgr(cnnacc_handle* h, const uint8_t* frames, int64_t n, int fh, int fw, uint8_t* gray128, uint32_t flags) {
@@ -1045,8 +1064,9 @@ int cnnacc_probe_int8_peak(cnnacc_handle* h, double target_ms, double* tops, dou
     const int iters = (int)std::min<double>(1 << 30, std::max<double>(iters0, want)) & ~7;
     if ((rc = run(iters, &ms))) { cudaFree(d_status); return rc; }
     int st = 0;
-    CU(h, cudaMemcpy(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    const cudaError_t e_st = cudaMemcpy(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(d_status);
+    CU(h, e_st);
     if (st) return fail(h, CNNACC_ERR_CUDA, "int8 peak probe timed out");
     *tops = (double)h->sm_count * iters * kProbeOpsPerMma / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms;
