@@ -11,6 +11,7 @@ CSRC = os.path.join(_DIR, "csrc")
 OK, ERR_TIMEOUT, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 FLAG_DEVICE_PTRS, FLAG_DIRECT, FLAG_KEEP_MAPS, FLAG_CLS_GIVEN, FLAG_BBOX_UPSAMPLED, FLAG_LOGITS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_TWO_KERNELS = 0x40
+MAX_PENDING = 8
 
 # every symbol include/cnnacc.h declares: name -> (restype, argtypes)
 _c = ctypes
@@ -30,6 +31,9 @@ SYMBOLS = {
     "cnnacc_pdl_chain_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "cnnacc_tile_plan_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "cnnacc_run_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
+    "cnnacc_run_batch_async": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32,
+                                          _c.POINTER(_c.c_int64)]),
+    "cnnacc_wait_batch": (_c.c_int, [_H, _c.c_int64]),
     "cnnacc_load_image": (_c.c_int, [_H, _c.c_void_p, _c.c_size_t]),
     "cnnacc_start": (_c.c_int, [_H]),
     "cnnacc_status": (_c.c_int, [_H]),

@@ -41,6 +41,14 @@ def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _item_bytes(x):
+    """Bytes per item of a batch [N, ...] (also for N == 0)."""
+    n = 1
+    for d in x.shape[1:]:
+        n *= int(d)
+    return n if len(x.shape) >= 2 else -1
+
+
 def register_host(array):
     """Page-lock a host array the caller owns (e.g. an np.memmap of a /dev/shm file shared by the per-GPU processes) so the
     copy engines can write into it directly.  Returns a callable that unregisters it."""
@@ -77,6 +85,7 @@ class CNNAccelerator:
         self._out_addr = 0
         self._n_cls = 0
         self._user_stream = 0
+        self._pending = {}
         self._one_ms = (ctypes.byref(ctypes.c_float()), ctypes.byref(ctypes.c_float()))
         self._finalizer = weakref.finalize(self, self._libc.cnnacc_destroy, self._h)
 
@@ -244,6 +253,29 @@ class CNNAccelerator:
         self._check(self._libc.cnnacc_run_batch(self._h, _vp(images), n, H, W, _vp(out), flags))
         return out
 
+    def run_batch_async(self, images, out=None):
+        """Queue one HOST batch (images [N,H,W] u8, C-contiguous, ideally from alloc_host) and return a ticket at once;
+        wait_batch(ticket) returns the features.  Batches complete in order and overlap each other's copies (cnnacc.h:
+        cnnacc_run_batch_async).  `images` and `out` must not be touched until the ticket was waited for."""
+        if not (isinstance(images, np.ndarray) and images.dtype == np.uint8 and images.flags.c_contiguous and images.ndim == 3):
+            raise ValueError("images must be a C-contiguous uint8 numpy array [N,H,W] (no implicit copy: the call returns before it is read)")
+        n, H, W = images.shape
+        if out is None:
+            out = alloc_host((n, 64, H // 8, W // 8), np.uint8)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.flags.c_contiguous and out.size == n * 64 * (H // 8) * (W // 8)):
+            raise ValueError("out must be a C-contiguous uint8 numpy array of n*64*(H/8)*(W/8) elements")
+        ticket = ctypes.c_int64(-1)
+        self._check(self._libc.cnnacc_run_batch_async(self._h, _vp(images), n, H, W, _vp(out), 0, ctypes.byref(ticket)))
+        self._pending[ticket.value] = (images, out)          # keep both alive while the copy engines use them
+        for t in [t for t in self._pending if t <= ticket.value - 4 * _lib.MAX_PENDING]:
+            del self._pending[t]                             # never waited for, and complete for a long time (cnnacc.h)
+        return ticket.value
+
+    def wait_batch(self, ticket):
+        """Block until the batch behind `ticket` is complete -> its features array."""
+        self._check(self._libc.cnnacc_wait_batch(self._h, int(ticket)))
+        return self._pending.pop(ticket, (None, None))[1]
+
     def load_classifier(self, fc_w, fc_b):
         fc_w = np.ascontiguousarray(fc_w, dtype=np.float32)
         fc_b = np.ascontiguousarray(fc_b, dtype=np.float32)
@@ -262,7 +294,7 @@ class CNNAccelerator:
         if _is_torch_cuda(x):
             import torch
             # the kernels read each item through 128-bit loads / a TMA box: shape, dtype and layout must be exact
-            if x.dtype != torch.uint8 or not x.is_contiguous() or x.dim() < 2 or x[0].numel() != 16384:
+            if x.dtype != torch.uint8 or not x.is_contiguous() or _item_bytes(x) != 16384:
                 raise ValueError("expected a contiguous CUDA uint8 tensor of [N,128,128] images or [N,64,256] features")
             n = x.shape[0]
             probs = torch.empty((n, self._n_cls), dtype=torch.float32, device=x.device)
@@ -274,9 +306,9 @@ class CNNAccelerator:
                                flags | _lib.FLAG_DEVICE_PTRS))
             return cls, probs, bbox
         x = np.ascontiguousarray(x, dtype=np.uint8)
-        n = x.shape[0]
-        if x[0].size != 16384:
+        if _item_bytes(x) != 16384:
             raise ValueError("expected [N,128,128] images or [N,64,256] features")
+        n = x.shape[0]
         probs = np.empty((n, self._n_cls), dtype=np.float32)
         cls = np.empty((n,), dtype=np.int32)
         bbox = np.empty((n, 4), dtype=np.int32)
@@ -292,9 +324,9 @@ class CNNAccelerator:
     def pool_features(self, features):
         """features [N,64,256] u8 -> [N,1024] f32 spatial-bin pooled, /255 (retrain_classifier.py:188-205): the trainer's input."""
         x = np.ascontiguousarray(features, dtype=np.uint8)
-        n = x.shape[0]
-        if x.ndim < 2 or x[0].size != 16384:
+        if _item_bytes(x) != 16384:
             raise ValueError("expected [N,64,256] features")
+        n = x.shape[0]
         out = np.empty((n, 1024), dtype=np.float32)
         self._check(self._libc.cnnacc_pool_features(self._h, _vp(x), n, _vp(out), 0))
         return out
@@ -306,8 +338,8 @@ class CNNAccelerator:
             raise RuntimeError("classifier not loaded")
         x = np.ascontiguousarray(features, dtype=np.uint8)
         cls = np.ascontiguousarray(cls, dtype=np.int32)
-        n = x.shape[0]
-        if x[0].size != 16384 or cls.shape != (n,):
+        n = x.shape[0] if x.ndim else -1
+        if _item_bytes(x) != 16384 or cls.shape != (n,):
             raise ValueError("expected [N,64,256] features and [N] classes")
         bbox = np.empty((n, 4), dtype=np.int32)
         cam = np.empty((n, 128, 128), dtype=np.uint8) if return_cam else None
@@ -320,8 +352,8 @@ class CNNAccelerator:
             raise RuntimeError("classifier not loaded")
         x = np.ascontiguousarray(features, dtype=np.uint8)
         cls = np.ascontiguousarray(cls, dtype=np.int32)
-        n = x.shape[0]
-        if x[0].size != 16384 or cls.shape != (n,):
+        n = x.shape[0] if x.ndim else -1
+        if _item_bytes(x) != 16384 or cls.shape != (n,):
             raise ValueError("expected [N,64,256] features and [N] classes")
         bbox = np.empty((n, 4), dtype=np.int32)
         self._check(self._libc.cnnacc_classify_batch(self._h, _vp(x), n, None, _vp(cls), _vp(bbox), _lib.FLAG_CLS_GIVEN))

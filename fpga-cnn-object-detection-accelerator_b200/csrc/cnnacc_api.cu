@@ -87,6 +87,10 @@ struct cnnacc_handle {
     bool image_loaded = false, started = false;
     int64_t launches = 0;
     PdlChain pdl;                                   // overlapped back-to-back conv-stack launches (pdl_chain.h)
+    // cnnacc_run_batch_async: completion events of the last kMaxPending submitted calls, and the ring position the staging
+    // slots continue from (asynchronous calls share one continuous ring across calls)
+    cudaEvent_t ev_ticket[CNNACC_MAX_PENDING] = {};
+    int64_t next_ticket = 0, ring_ci = 0;
     std::string err;
 };
 
@@ -344,6 +348,71 @@ int check_ready(cnnacc_handle* h) {
     return 0;
 }
 
+// The host-pointer conv stack: queue the staged copies and kernels of one call on the ring; does not wait for anything.
+// `pipelined`: the call belongs to a stream of asynchronous calls -- no ramped chunk sizes (the neighbouring calls keep both
+// copy directions busy at its edges) and the slots continue from where the previous call left the ring.
+int enqueue_host_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, int W, uint8_t* feats, uint32_t flags, bool pipelined) {
+    int rc;
+    const size_t in_sz = (size_t)H * W, out_sz = (size_t)64 * (H / 8) * (W / 8);
+    const bool maps = needs_maps(h, H, W, flags);
+    // host pointers: a ring of kSlots staging buffers driven through one stream per engine (H2D copies, kernels, D2H copies),
+    // chained by per-slot events, so copies in both directions and the kernels overlap.  (One stream per slot measured the
+    // same or slightly worse; more than 4 slots made no difference: profiles/r1_e2e_chunk_sweep.txt.)
+    // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
+    // chunks; each chunk costs ~20-40 us of cross-engine hand-offs on top of its copies (tools/probe_pipeline.cu shows
+    // the same for any H2D -> kernel -> D2H chain), so they should not be small either: a quarter of the call, clamped
+    // to 4..32 MiB (tools/e2e_chunk_sweep.sh; CNNACC_HOST_CHUNK_MB overrides).
+    static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
+    size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
+    // In a stream of calls the neighbours cover a call's edges, so only the hand-off cost counts: one chunk per call up to
+    // 64 MiB (profiles/r2_e2e_stream_sweep.txt: 2.85 M img/s at 64 MiB, 2.77 M at 32, 2.60 M at 16, batch 4096, 3 in flight).
+    if (pipelined && !chunk_mb) chunk_bytes = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz));
+    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
+    if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
+    // Chunk sizes ramp up at the start and down at the end (1/4, 1/2, 1, ..., 1, 1/2, 1/4 of hchunk for depth 2): the first
+    // H2D and the last D2H run alone on the link, so the shorter they are the sooner both directions are busy together.
+    static const int ramp = [] { const char* e = getenv("CNNACC_HOST_RAMP"); int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
+    const int depth = (!pipelined && n >= 4 * hchunk && (hchunk >> ramp) >= 1) ? ramp : 0;
+    const int64_t tail_total = hchunk - (hchunk >> depth);                           // h/2 + h/4 + ... + h/2^depth
+    if (pipelined) {
+        // earlier calls may still be using the slots: growing one (free + malloc) waits for the device first
+        bool grows = false;
+        for (const Slot& s : h->slots) grows |= s.cap_in < hchunk * in_sz || s.cap_out < hchunk * out_sz;
+        if (grows) CU(h, cudaDeviceSynchronize());
+    }
+    const int64_t ring0 = pipelined ? h->ring_ci : 0;                                // where this call enters the slot ring
+    int64_t ci = 0, m = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += m, ci++) {
+        m = hchunk;
+        if (depth) {
+            const int64_t left = n - i0;
+            if (ci < depth) m = hchunk >> (depth - ci);                              // ramp up
+            else if (left <= tail_total) {                                           // ramp down: largest h/2^j that fits, remainder first
+                int64_t piece = hchunk >> 1, rest = tail_total;
+                while (piece > 1 && left <= rest - piece) { rest -= piece; piece >>= 1; }
+                m = left - (rest - piece);
+            } else if (left < hchunk + tail_total) m = left - tail_total;            // the last full-size piece takes the remainder
+            m = std::max<int64_t>(m, 1);
+        }
+        m = std::min(m, n - i0);
+        Slot& s = h->slots[(ring0 + ci) % kSlots];
+        if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
+        // slot drained (its kernels ended earlier); in a pipelined stream its last user may be an earlier call (an event that
+        // was never recorded counts as complete)
+        if (ci >= kSlots || pipelined) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));
+        CU(h, cudaMemcpyAsync(s.d_in, imgs + i0 * in_sz, m * in_sz, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
+        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
+        if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, H, W, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
+        CU(h, cudaEventRecord(s.ev_k, h->st_k));
+        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
+        CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
+    }
+    if (pipelined) h->ring_ci = (ring0 + ci) % kSlots;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -383,6 +452,8 @@ int cnnacc_create(int device_id, cnnacc_handle** out) {
         for (auto ev : {&s.ev_in, &s.ev_k, &s.ev_out})
             if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
+    for (auto& ev : h->ev_ticket)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (auto st : {&h->st_h2d, &h->st_k, &h->st_d2h})
         if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaHostAlloc(&h->h_img, CNNACC_IMG * CNNACC_IMG, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
@@ -410,6 +481,7 @@ int cnnacc_destroy(cnnacc_handle* h) {
         for (auto ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     }
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) if (st) cudaStreamDestroy(st);
+    for (auto ev : h->ev_ticket) if (ev) cudaEventDestroy(ev);
     cudaFree(h->d_prep_start); cudaFree(h->d_prep_cnt); cudaFree(h->d_prep_alpha); cudaFree(h->d_gray);
     cudaFree(h->d_pil_kx); cudaFree(h->d_pil_bx); cudaFree(h->d_pil_ky); cudaFree(h->d_pil_by);
     cudaFree(h->d_pil_tmp); cudaFree(h->d_pil_in); cudaFree(h->d_pil_out);
@@ -526,53 +598,44 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
         return CNNACC_OK;
     }
 
-    // host pointers: a ring of kSlots staging buffers driven through one stream per engine (H2D copies, kernels, D2H copies),
-    // chained by per-slot events, so copies in both directions and the kernels overlap.  (One stream per slot measured the
-    // same or slightly worse; more than 4 slots made no difference: profiles/r1_e2e_chunk_sweep.txt.)
+    // host pointers: returns when feats is complete
     CU(h, cudaStreamSynchronize(h->stream));
-    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));   // idle already (RingDrain)
+    for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));   // idle already unless asynchronous calls are pending
     RingDrain drain(h);
-    // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
-    // chunks; each chunk costs ~20-40 us of cross-engine hand-offs on top of its copies (tools/probe_pipeline.cu shows
-    // the same for any H2D -> kernel -> D2H chain), so they should not be small either: a quarter of the call, clamped
-    // to 4..32 MiB (tools/e2e_chunk_sweep.sh; CNNACC_HOST_CHUNK_MB overrides).
-    static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
-    size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
-    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
-    if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
-    // Chunk sizes ramp up at the start and down at the end (1/4, 1/2, 1, ..., 1, 1/2, 1/4 of hchunk for depth 2): the first
-    // H2D and the last D2H run alone on the link, so the shorter they are the sooner both directions are busy together.
-    static const int ramp = [] { const char* e = getenv("CNNACC_HOST_RAMP"); int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
-    const int depth = (n >= 4 * hchunk && (hchunk >> ramp) >= 1) ? ramp : 0;
-    const int64_t tail_total = hchunk - (hchunk >> depth);                           // h/2 + h/4 + ... + h/2^depth
-    int64_t ci = 0, m = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += m, ci++) {
-        m = hchunk;
-        if (depth) {
-            const int64_t left = n - i0;
-            if (ci < depth) m = hchunk >> (depth - ci);                              // ramp up
-            else if (left <= tail_total) {                                           // ramp down: largest h/2^j that fits, remainder first
-                int64_t piece = hchunk >> 1, rest = tail_total;
-                while (piece > 1 && left <= rest - piece) { rest -= piece; piece >>= 1; }
-                m = left - (rest - piece);
-            } else if (left < hchunk + tail_total) m = left - tail_total;            // the last full-size piece takes the remainder
-            m = std::max<int64_t>(m, 1);
-        }
-        m = std::min(m, n - i0);
-        Slot& s = h->slots[ci % kSlots];
-        if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
-        if (ci >= kSlots) CU(h, cudaStreamWaitEvent(h->st_h2d, s.ev_out, 0));       // slot drained (its kernels ended earlier)
-        CU(h, cudaMemcpyAsync(s.d_in, imgs + i0 * in_sz, m * in_sz, cudaMemcpyHostToDevice, h->st_h2d));
-        CU(h, cudaEventRecord(s.ev_in, h->st_h2d));
-        CU(h, cudaStreamWaitEvent(h->st_k, s.ev_in, 0));
-        if ((rc = conv_stack_device(h, h->st_k, s.d_in, m, H, W, s.d_out, flags, h->d_l0, h->d_l1))) return rc;
-        CU(h, cudaEventRecord(s.ev_k, h->st_k));
-        CU(h, cudaStreamWaitEvent(h->st_d2h, s.ev_k, 0));
-        CU(h, cudaMemcpyAsync(feats + i0 * out_sz, s.d_out, m * out_sz, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(h, cudaEventRecord(s.ev_out, h->st_d2h));
-    }
+    if ((rc = enqueue_host_batch(h, imgs, n, H, W, feats, flags, /*pipelined=*/false))) return rc;
     CU(h, cudaStreamSynchronize(h->st_d2h));            // the last D2H is the last operation of the whole chain
     return drain.done(check_fused_status(h));
+}
+
+int cnnacc_run_batch_async(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, int W, uint8_t* feats, uint32_t flags,
+                           int64_t* ticket) {
+    int rc;
+    if ((rc = check_ready(h))) return rc;
+    if (!ticket) return fail(h, CNNACC_ERR_ARG, "ticket is NULL");
+    if (n < 0 || !valid_hw(H, W)) return fail(h, CNNACC_ERR_ARG, "bad n / H / W (H, W must be multiples of 16)");
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) return fail(h, CNNACC_ERR_ARG, "device-pointer calls are asynchronous already (cnnacc_run_batch)");
+    if (n > 0 && (!imgs || !feats)) return fail(h, CNNACC_ERR_ARG, "NULL image / feature pointer");
+    // the per-layer kernels share two workspaces between chunks; only the paths without them can overlap calls
+    if (needs_maps(h, H, W, flags)) return fail(h, CNNACC_ERR_ARG, "this size / flag combination has no asynchronous form: use cnnacc_run_batch");
+    CU(h, cudaSetDevice(h->device));
+    // the event of the call submitted CNNACC_MAX_PENDING calls ago is about to be reused: that call must have completed
+    cudaEvent_t ev = h->ev_ticket[h->next_ticket % CNNACC_MAX_PENDING];
+    if (h->next_ticket >= CNNACC_MAX_PENDING) CU(h, cudaEventSynchronize(ev));
+    RingDrain drain(h);
+    if (n > 0 && (rc = enqueue_host_batch(h, imgs, n, H, W, feats, flags, /*pipelined=*/true))) return rc;
+    CU(h, cudaEventRecord(ev, h->st_d2h));
+    *ticket = h->next_ticket++;
+    return drain.done(CNNACC_OK);
+}
+
+int cnnacc_wait_batch(cnnacc_handle* h, int64_t ticket) {
+    if (!h) return CNNACC_ERR_ARG;
+    if (ticket < 0 || ticket >= h->next_ticket) return fail(h, CNNACC_ERR_ARG, "unknown ticket");
+    CU(h, cudaSetDevice(h->device));
+    // calls complete in submission order and an event is reused only after its call has completed
+    if (ticket + CNNACC_MAX_PENDING >= h->next_ticket)         // older tickets: their event has been reused, i.e. they are complete
+        CU(h, cudaEventSynchronize(h->ev_ticket[ticket % CNNACC_MAX_PENDING]));
+    return check_fused_status(h);
 }
 
 int cnnacc_load_image(cnnacc_handle* h, const uint8_t* img, size_t n) {

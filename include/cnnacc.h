@@ -116,6 +116,20 @@ int cnnacc_tile_plan_host(int n_out, int *origin, int *first, int *end, int cap)
 int cnnacc_run_batch(cnnacc_handle *h, const uint8_t *imgs, int64_t n, int H, int W,
                      uint8_t *feats, uint32_t flags);
 
+/* The same call for a STREAM of host batches (the camera loop of realtime_detect.py:575-598 turned into a pipeline):
+ * cnnacc_run_batch_async queues the staged copies and kernels of one batch of HOST buffers and returns a ticket at once;
+ * cnnacc_wait_batch(ticket) returns when that batch's features are in `feats`.  Batches complete in submission order and share
+ * one staging ring, so the H2D of batch k+1 overlaps the kernels and the D2H of batch k (a synchronous call leaves the link idle
+ * in one direction during its first H2D and its last D2H).  imgs / feats should be page-locked (cnnacc_alloc_host /
+ * cnnacc_register_host; pageable memory makes the copies synchronous) and must stay untouched until the ticket was waited for.
+ * At most CNNACC_MAX_PENDING batches are outstanding: submitting one more first waits for the oldest.  Any synchronous
+ * host-pointer call, cnnacc_synchronize and cnnacc_destroy wait for everything pending.  Sizes / flags that need the per-layer
+ * workspaces (sides below 128, CNNACC_FLAG_DIRECT, CNNACC_FLAG_KEEP_MAPS) have no asynchronous form (CNNACC_ERR_ARG). */
+#define CNNACC_MAX_PENDING 8
+int cnnacc_run_batch_async(cnnacc_handle *h, const uint8_t *imgs, int64_t n, int H, int W,
+                           uint8_t *feats, uint32_t flags, int64_t *ticket);
+int cnnacc_wait_batch(cnnacc_handle *h, int64_t ticket);
+
 /* ---- single-image register-style protocol (CNNAccelerator / fast_readout.c) ----------------
  * load_image   : DMA of one 128x128 image into input BRAM        (pynq_inference.py:209-224)
  * start        : control reg bit 0                                (pynq_inference.py:231-234)

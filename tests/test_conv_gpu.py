@@ -438,3 +438,59 @@ def test_back_to_back_launches_with_and_without_dependencies(fc, port, shipped_w
         assert np.array_equal(third.cpu().numpy(), want2) and np.array_equal(outs[2].cpu().numpy(), want[2])
         b.close()
     a.close()
+
+
+def test_asynchronous_host_batches(fc, port, shipped_weights):
+    """cnnacc_run_batch_async / cnnacc_wait_batch: a stream of host batches through one staging ring.  Every batch equals the
+    oracle whatever the submission depth, the wait order, the batch sizes (slot growth in mid-stream) and the calls mixed in."""
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    a.set_shifts(7, 10, 11)
+    sizes = [300, 300, 300, 1200, 1, 300, 2048, 300, 300, 300, 700, 300]           # 12 > CNNACC_MAX_PENDING batches in flight
+    h_in = [fc.alloc_host((n, 128, 128)) for n in sizes]
+    h_out = [fc.alloc_host((n, 64, 16, 16)) for n in sizes]
+    for i, n in enumerate(sizes):
+        h_in[i][:] = inputs.make_images(("rng", 7000 + i), n)
+        h_out[i][:] = 0xEE
+    want = [oracle.port_infer_batch(port, x, shipped_weights, (7, 10, 11)) for x in h_in]
+    tickets = [a.run_batch_async(x, out=y) for x, y in zip(h_in, h_out)]           # all submitted before any wait
+    assert tickets == list(range(len(sizes)))
+    for i in (5, 0, 11, 3):                                                         # any order; older ones are complete by then
+        out = a.wait_batch(tickets[i])
+        assert out is h_out[i]
+    a.synchronize()
+    for i, n in enumerate(sizes):
+        assert np.array_equal(h_out[i].reshape(n, 64, 256), want[i]), i
+    # depth-2 streaming loop (the bench's e2e leg), a synchronous call and a device-pointer call in mid-stream, 512x512 batches
+    import torch
+    prev = None
+    for rep in range(6):
+        i = rep % 3
+        h_out[i][:] = 0
+        t = a.run_batch_async(h_in[i], out=h_out[i])
+        if rep == 2:
+            got = a.run_batch(h_in[4])                                              # synchronous: drains the ring first
+            assert np.array_equal(got.reshape(1, 64, 256), want[4])
+        if rep == 4:
+            d = a.run_batch(torch.from_numpy(np.ascontiguousarray(h_in[4])).cuda())
+            assert np.array_equal(d.cpu().numpy().reshape(1, 64, 256), want[4])
+        if prev is not None:
+            j, tp = prev
+            assert np.array_equal(a.wait_batch(tp).reshape(-1, 64, 256), want[j]), rep
+        prev = (i, t)
+    assert np.array_equal(a.wait_batch(prev[1]).reshape(-1, 64, 256), want[prev[0]])
+    big = fc.alloc_host((3, 512, 512))
+    big[:] = np.random.default_rng(9).integers(0, 256, big.shape, dtype=np.uint8)
+    tb = [a.run_batch_async(big) for _ in range(2)]
+    outs = [a.wait_batch(t) for t in tb]
+    assert outs[0].shape == (3, 64, 64, 64) and np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], a.run_batch(big))
+    # argument errors: unknown ticket, sizes that need the per-layer workspaces, arrays that would need a copy
+    with pytest.raises(ValueError):
+        a.wait_batch(10 ** 6)
+    with pytest.raises(ValueError):
+        a.run_batch_async(np.zeros((2, 64, 64), np.uint8))
+    with pytest.raises(ValueError):
+        a.run_batch_async(np.zeros((2, 128, 256), np.uint8)[:, :, ::2])
+    t0 = a.run_batch_async(np.zeros((0, 128, 128), np.uint8))                      # empty batch: a ticket that is complete
+    assert a.wait_batch(t0).shape == (0, 64, 16, 16)
+    a.close()

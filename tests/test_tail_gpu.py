@@ -329,3 +329,27 @@ def test_classifier_weight_domain(acc):
     w2[3, 500] = np.float32(2.0 ** 99)
     acc.load_classifier(w2, b)                      # accepted
     acc.load_classifier(w, b)
+
+
+def test_empty_and_misshapen_batches(acc, shipped_weights):
+    """n = 0 goes through every prediction entry point (host and device pointers); wrong item sizes raise before any launch."""
+    import torch
+    acc.load_weights(shipped_weights)
+    e = np.zeros((0, 64, 256), np.uint8)
+    for cls, probs, bbox in (acc.classify_batch(e), acc.infer_batch(np.zeros((0, 128, 128), np.uint8)),
+                             acc.infer_batch(torch.zeros((0, 128, 128), dtype=torch.uint8, device="cuda"))):
+        assert tuple(cls.shape) == (0,) and tuple(probs.shape) == (0, 6) and tuple(bbox.shape) == (0, 4)
+    assert acc.pool_features(e).shape == (0, 1024)
+    assert acc.bbox_batch(e, np.zeros(0, np.int32)).shape == (0, 4)
+    assert acc.cam_bbox_batch(e, np.zeros(0, np.int32)).shape == (0, 4)
+    n0 = acc.launch_count
+    for bad in (np.zeros((2, 64, 255), np.uint8), np.zeros(16384, np.uint8), np.zeros((0, 100), np.uint8)):
+        with pytest.raises(ValueError):
+            acc.classify_batch(bad)
+        with pytest.raises(ValueError):
+            acc.pool_features(bad)
+    with pytest.raises(ValueError):
+        acc.infer_batch(torch.zeros((3, 128, 127), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        acc.bbox_batch(np.zeros((2, 64, 256), np.uint8), np.zeros(3, np.int32))
+    assert acc.launch_count == n0
