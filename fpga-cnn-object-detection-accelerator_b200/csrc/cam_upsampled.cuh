@@ -17,7 +17,7 @@
 // sorted elements 11468 and 11469 (0.7 * 16383 = 11468.1) and so lands in [k_lo/255, k_hi/255), and 51/255 == 0.2f; hence
 // mask = level > max(k_lo, 51) with k_lo = the level of sorted[11468] (oracle/np_oracle.py get_cam_bbox_levels, checked
 // against the float formulation in tests/test_oracle.py).  k_lo comes from an 8-step bisection on "how many levels <= mid",
-// each thread counting over the 64 output pixels it keeps in registers.
+// each thread counting over the 64 output pixels it keeps in registers (four per SIMD-in-word compare).
 #pragma once
 #include <cmath>
 #include "common.cuh"
@@ -160,12 +160,13 @@ cam_bbox_upsampled_kernel(const uint8_t* __restrict__ feats, const float* __rest
 #pragma unroll 1
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        int c = 0;
+        // four pixels per compare: __vsetgtu4 leaves 1 in every byte lane whose pixel is > mid; the lanes add up over the 16
+        // words without carrying (<= 16 each) and dp4a sums them
+        const uint32_t mid4 = (uint32_t)mid * 0x01010101u;
+        uint32_t gt4 = 0;
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t v = up[i];
-            c += ((int)(v & 255u) <= mid) + ((int)((v >> 8) & 255u) <= mid) + ((int)((v >> 16) & 255u) <= mid) + ((int)(v >> 24) <= mid);
-        }
+        for (int i = 0; i < 16; i++) gt4 += __vsetgtu4(up[i], mid4);
+        int c = 64 - (int)__dp4a(gt4, 0x01010101u, 0u);       // pixels <= mid among this thread's 64
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
         __syncthreads();                                   // previous round's readers of s_cnt are done
@@ -178,15 +179,19 @@ cam_bbox_upsampled_kernel(const uint8_t* __restrict__ feats, const float* __rest
     }
     const int thr = max(lo, 51);                           // max(threshold, 0.2): 51/255 == 0.2f
 
+    // box of the pixels > thr: per word a byte-lane mask (0xFF where the pixel is above); the OR of the masks gives the thread's
+    // columns, the first / last non-empty word its rows (yy grows with i)
     int bx0 = kCamOut, by0 = kCamOut, bx1 = -1, by1 = -1;
+    const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
+    uint32_t cols = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const uint32_t v = up[i];
+        const uint32_t m4 = __vcmpgtu4(up[i], thr4);
         const int yy = warp + 8 * i;
-#pragma unroll
-        for (int b = 0; b < 4; b++)
-            if ((int)((v >> (8 * b)) & 255u) > thr) { bx0 = min(bx0, xq + b); bx1 = max(bx1, xq + b); by0 = min(by0, yy); by1 = max(by1, yy); }
+        cols |= m4;
+        if (m4) { by0 = min(by0, yy); by1 = yy; }
     }
+    if (cols) { bx0 = xq + ((__ffs((int)cols) - 1) >> 3); bx1 = xq + ((31 - __clz((int)cols)) >> 3); }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, off)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, off));
