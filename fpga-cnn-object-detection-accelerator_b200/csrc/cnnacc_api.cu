@@ -116,6 +116,15 @@ int grow(cnnacc_handle* h, uint8_t** p, size_t* cap, size_t need) {
     return 0;
 }
 
+// Device pointers go straight into TMA descriptors, bulk stores and 128-bit loads / stores: a misaligned one would fault the
+// whole context, so it is refused here.  (Host pointers are copied into the library's own aligned staging buffers.)
+bool aligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+#define REQUIRE_ALIGNED(h, p, a, what)                                                                           \
+    do {                                                                                                         \
+        if ((p) && !aligned((p), (a)))                                                                           \
+            return fail((h), CNNACC_ERR_ARG, std::string(what) + " device pointer must be " #a "-byte aligned"); \
+    } while (0)
+
 bool valid_hw(int H, int W) { return H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && H <= 8192 && W <= 8192; }
 
 // Sizes from 128 up (other than 128x128 itself) run as overlapping windows through the fused kernel.
@@ -589,6 +598,8 @@ int cnnacc_run_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, in
     const int64_t chunk = maps ? std::min<int64_t>(n, chunk_images(H, W)) : n;
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        REQUIRE_ALIGNED(h, imgs, 16, "image");
+        REQUIRE_ALIGNED(h, feats, 16, "feature");
         if (maps && (rc = ensure_maps(h, chunk, H, W))) return rc;
         for (int64_t i0 = 0; i0 < n; i0 += chunk) {
             const int64_t m = std::min(chunk, n - i0);
@@ -838,6 +849,10 @@ static int predict_impl(cnnacc_handle* h, const uint8_t* src, int64_t n, bool sr
     const bool feat_ws = src_is_images && infer_needs_feat_ws(h, upsampled, flags);
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        REQUIRE_ALIGNED(h, src, 16, "image / feature");
+        REQUIRE_ALIGNED(h, bbox, 16, "bbox");
+        REQUIRE_ALIGNED(h, probs, 4, "probs");
+        REQUIRE_ALIGNED(h, cls, 4, "cls");
         // one fused launch covers the whole call unless a workspace bounds the chunk
         static const int64_t ws_chunk = [] { const char* e = getenv("CNNACC_WS_CHUNK"); int v = e ? atoi(e) : 0; return (int64_t)(v > 0 ? v : 16384); }();
         const int64_t chunk = feat_ws ? std::min<int64_t>(n, ws_chunk) : n;
@@ -937,6 +952,8 @@ int cnnacc_pool_features(cnnacc_handle* h, const uint8_t* feats, int64_t n, floa
     CU(h, cudaSetDevice(h->device));
     const size_t feat_sz = CNNACC_FEAT_BYTES, out_sz = 1024 * sizeof(float);
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        REQUIRE_ALIGNED(h, feats, 16, "feature");
+        REQUIRE_ALIGNED(h, pooled, 16, "pooled");
         pool_features_kernel<<<(unsigned)n, 256, 0, h->stream>>>(feats, pooled);
         h->launches++;
         CU(h, cudaGetLastError());
@@ -977,7 +994,13 @@ int cnnacc_cam_bbox_batch(cnnacc_handle* h, const uint8_t* feats, int64_t n, con
     if (!feats || !cls || (!bbox && !cam)) return fail(h, CNNACC_ERR_ARG, "NULL feature / class pointer, or nothing to write");
     CU(h, cudaSetDevice(h->device));
     const size_t feat_sz = CNNACC_FEAT_BYTES, cam_sz = (size_t)kCamOut * kCamOut;
-    if (flags & CNNACC_FLAG_DEVICE_PTRS) return launch_cam_upsampled(h, h->stream, feats, n, cls, bbox, cam);
+    if (flags & CNNACC_FLAG_DEVICE_PTRS) {
+        REQUIRE_ALIGNED(h, feats, 16, "feature");
+        REQUIRE_ALIGNED(h, bbox, 16, "bbox");
+        REQUIRE_ALIGNED(h, cam, 4, "cam");
+        REQUIRE_ALIGNED(h, cls, 4, "cls");
+        return launch_cam_upsampled(h, h->stream, feats, n, cls, bbox, cam);
+    }
 
     CU(h, cudaStreamSynchronize(h->stream));
     for (auto st : {h->st_h2d, h->st_k, h->st_d2h}) CU(h, cudaStreamSynchronize(st));
@@ -1033,6 +1056,10 @@ static int frames_impl(cnnacc_handle* h, const uint8_t* frames, int64_t n, int f
 
     if (flags & CNNACC_FLAG_DEVICE_PTRS) {
         if (detect && upsampled && bbox && !cls) return fail(h, CNNACC_ERR_ARG, "CNNACC_FLAG_BBOX_UPSAMPLED with device pointers needs a cls array");
+        REQUIRE_ALIGNED(h, gray128, 16, "gray128");
+        REQUIRE_ALIGNED(h, bbox, 16, "bbox");
+        REQUIRE_ALIGNED(h, probs, 4, "probs");
+        REQUIRE_ALIGNED(h, cls, 4, "cls");
         const int64_t chunk = std::min<int64_t>(n, 16384);
         uint8_t* g = gray128;
         if (!g) { if ((rc = grow(h, &h->d_gray, &h->cap_gray, (size_t)chunk * img_sz))) return rc; }

@@ -14,6 +14,10 @@
  *   -4  not initialised: no weights / no classifier / no image loaded          (Python: RuntimeError)
  * There is no CPU fallback: without a CUDA device every call that computes returns -3.
  *
+ * Pointers: host pointers may have any alignment (they are copied through the library's own staging buffers).  With
+ * CNNACC_FLAG_DEVICE_PTRS the image / feature / gray128 / bbox / pooled pointers must be 16-byte aligned and the probs / cls /
+ * cam pointers 4-byte aligned (they feed TMA descriptors, bulk stores and 128-bit accesses); anything else returns -2.
+ *
  * Threading: one handle = one device + one stream.  A handle is not thread-safe (neither is the
  * reference: arm_cnn.c:30-32 static scratch); distinct handles are independent.
  */

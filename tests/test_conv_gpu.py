@@ -494,3 +494,28 @@ def test_asynchronous_host_batches(fc, port, shipped_weights):
     t0 = a.run_batch_async(np.zeros((0, 128, 128), np.uint8))                      # empty batch: a ticket that is complete
     assert a.wait_batch(t0).shape == (0, 64, 16, 16)
     a.close()
+
+
+def test_misaligned_device_pointers_are_refused(fc, shipped_weights):
+    """Device pointers feed TMA descriptors and 128-bit accesses: a misaligned one is a ValueError, not a faulted context."""
+    import torch
+    a = fc.CNNAccelerator()
+    a.load_weights(shipped_weights)
+    w, b = inputs.make_fc()
+    a.load_classifier(w, b)
+    raw = torch.zeros(3 * 16384 + 64, dtype=torch.uint8, device="cuda")
+    good = raw[:2 * 16384].view(2, 128, 128)
+    bad = raw[4:4 + 2 * 16384].view(2, 128, 128)                        # contiguous, 4 bytes off
+    n0 = a.launch_count
+    with pytest.raises(ValueError):
+        a.run_batch(bad)
+    with pytest.raises(ValueError):
+        a.run_batch(good, out=torch.zeros(2 * 16384 + 16, dtype=torch.uint8, device="cuda")[8:8 + 2 * 16384].view(2, 64, 16, 16))
+    with pytest.raises(ValueError):
+        a.infer_batch(bad)
+    with pytest.raises(ValueError):
+        a.classify_batch(bad.view(2, 64, 256))
+    assert a.launch_count == n0
+    assert a.run_batch(good).shape == (2, 64, 16, 16)                    # the context is intact
+    a.synchronize()
+    a.close()
