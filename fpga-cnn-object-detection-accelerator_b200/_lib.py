@@ -29,6 +29,7 @@ SYMBOLS = {
     "cnnacc_get_accumulator_bits": (_c.c_int, [_H]),
     "cnnacc_pack_weights_host": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "cnnacc_pdl_chain_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "cnnacc_chunk_plan_host": (_c.c_int, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int]),
     "cnnacc_tile_plan_host": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "cnnacc_run_batch": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32]),
     "cnnacc_run_batch_async": (_c.c_int, [_H, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_uint32,

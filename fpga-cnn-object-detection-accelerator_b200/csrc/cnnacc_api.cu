@@ -18,6 +18,7 @@
 #include "cam_upsampled.cuh"
 #include "preprocess.cuh"
 #include "pil_resize.cuh"
+#include "host_chunks.h"
 #include "pdl_chain.h"
 #include "tiling.cuh"
 #include "weights_pack.h"
@@ -364,25 +365,12 @@ int enqueue_host_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, 
     int rc;
     const size_t in_sz = (size_t)H * W, out_sz = (size_t)64 * (H / 8) * (W / 8);
     const bool maps = needs_maps(h, H, W, flags);
-    // host pointers: a ring of kSlots staging buffers driven through one stream per engine (H2D copies, kernels, D2H copies),
-    // chained by per-slot events, so copies in both directions and the kernels overlap.  (One stream per slot measured the
-    // same or slightly worse; more than 4 slots made no difference: profiles/r1_e2e_chunk_sweep.txt.)
-    // chunk = what one slot stages.  The first H2D and the last D2H cannot overlap anything, so a call wants at least ~4
-    // chunks; each chunk costs ~20-40 us of cross-engine hand-offs on top of its copies (tools/probe_pipeline.cu shows
-    // the same for any H2D -> kernel -> D2H chain), so they should not be small either: a quarter of the call, clamped
-    // to 4..32 MiB (tools/e2e_chunk_sweep.sh; CNNACC_HOST_CHUNK_MB overrides).
+    // the cut into staging chunks: host_chunks.h (CNNACC_HOST_CHUNK_MB / CNNACC_HOST_RAMP override it)
     static const size_t chunk_mb = [] { const char* e = getenv("CNNACC_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 0); }();
-    size_t chunk_bytes = chunk_mb ? (chunk_mb << 20) : std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz / 4));
-    // In a stream of calls the neighbours cover a call's edges, so only the hand-off cost counts: one chunk per call up to
-    // 64 MiB (profiles/r2_e2e_stream_sweep.txt: 2.85 M img/s at 64 MiB, 2.77 M at 32, 2.60 M at 16, batch 4096, 3 in flight).
-    if (pipelined && !chunk_mb) chunk_bytes = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)4 << 20, (size_t)n * in_sz));
-    const int64_t hchunk = std::min<int64_t>(n, std::max<int64_t>(1, std::min<int64_t>(chunk_images(H, W), (int64_t)(chunk_bytes / in_sz))));
-    if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
-    // Chunk sizes ramp up at the start and down at the end (1/4, 1/2, 1, ..., 1, 1/2, 1/4 of hchunk for depth 2): the first
-    // H2D and the last D2H run alone on the link, so the shorter they are the sooner both directions are busy together.
     static const int ramp = [] { const char* e = getenv("CNNACC_HOST_RAMP"); int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 4 ? 4 : v); }();
-    const int depth = (!pipelined && n >= 4 * hchunk && (hchunk >> ramp) >= 1) ? ramp : 0;
-    const int64_t tail_total = hchunk - (hchunk >> depth);                           // h/2 + h/4 + ... + h/2^depth
+    const HostChunkPlan plan = make_host_chunk_plan(n, in_sz, chunk_images(H, W), pipelined, chunk_mb, ramp);
+    const int64_t hchunk = plan.full;
+    if (maps && (rc = ensure_maps(h, hchunk, H, W))) return rc;
     if (pipelined) {
         // earlier calls may still be using the slots: growing one (free + malloc) waits for the device first
         bool grows = false;
@@ -392,18 +380,7 @@ int enqueue_host_batch(cnnacc_handle* h, const uint8_t* imgs, int64_t n, int H, 
     const int64_t ring0 = pipelined ? h->ring_ci : 0;                                // where this call enters the slot ring
     int64_t ci = 0, m = 0;
     for (int64_t i0 = 0; i0 < n; i0 += m, ci++) {
-        m = hchunk;
-        if (depth) {
-            const int64_t left = n - i0;
-            if (ci < depth) m = hchunk >> (depth - ci);                              // ramp up
-            else if (left <= tail_total) {                                           // ramp down: largest h/2^j that fits, remainder first
-                int64_t piece = hchunk >> 1, rest = tail_total;
-                while (piece > 1 && left <= rest - piece) { rest -= piece; piece >>= 1; }
-                m = left - (rest - piece);
-            } else if (left < hchunk + tail_total) m = left - tail_total;            // the last full-size piece takes the remainder
-            m = std::max<int64_t>(m, 1);
-        }
-        m = std::min(m, n - i0);
+        m = plan.next(i0, ci);
         Slot& s = h->slots[(ring0 + ci) % kSlots];
         if ((rc = slot_reserve(h, s, hchunk * in_sz, hchunk * out_sz, 0))) return rc;
         // slot drained (its kernels ended earlier); in a pipelined stream its last user may be an earlier call (an event that
@@ -570,6 +547,19 @@ int cnnacc_pdl_chain_host(int n_launches, const uint64_t* ranges, const int64_t*
         launches++;
     }
     return CNNACC_OK;
+}
+
+int cnnacc_chunk_plan_host(int64_t n, int H, int W, int pipelined, int64_t* sizes, int cap) {
+    if (n < 1 || !valid_hw(H, W) || !sizes || cap < 1) return CNNACC_ERR_ARG;
+    const HostChunkPlan plan = make_host_chunk_plan(n, (size_t)H * W, chunk_images(H, W), pipelined != 0, 0, 2);
+    int count = 0;
+    for (int64_t i0 = 0; i0 < n; count++) {
+        const int64_t m = plan.next(i0, count);
+        if (count >= cap) return CNNACC_ERR_ARG;
+        sizes[count] = m;
+        i0 += m;
+    }
+    return count;
 }
 
 int cnnacc_tile_plan_host(int n_out, int* origin, int* first, int* end, int cap) {

@@ -110,6 +110,11 @@ int cnnacc_pdl_chain_host(int n_launches, const uint64_t *ranges, const int64_t 
  * (layer_fsm.v:66-75,205-213); tests/ check that the plan owns every output exactly once and only where it is valid. */
 int cnnacc_tile_plan_host(int n_out, int *origin, int *first, int *end, int cap);
 
+/* Host-only view of how a host-pointer cnnacc_run_batch (pipelined = 0) or cnnacc_run_batch_async (pipelined = 1) call of n
+ * H x W images is cut into staging chunks (csrc/host_chunks.h): sizes[i] = images in chunk i.  Returns the number of chunks
+ * (<= cap) or a negative code.  No GPU needed; tests/ check that every plan covers the call exactly once. */
+int cnnacc_chunk_plan_host(int64_t n, int H, int W, int pipelined, int64_t *sizes, int cap);
+
 /* ---- the hot path: batched conv stack ------------------------------------------------------
  * Replaces cnn_infer (arm_cnn.c:159-198) / FPGAEngine.run (realtime_detect.py:313-363) for n images.
  *   imgs  : [n][H][W] u8          feats : [n][64][H/8][W/8] u8   (CHW per image, arm_cnn.c:64-65)

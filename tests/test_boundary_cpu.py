@@ -128,3 +128,46 @@ def test_overlapped_launch_bookkeeping():
     assert _pdl([L(0, 1), L(2, 3, stream=8), L(4, 5, stream=8)]) == [1, 1, 0]
     # 8. after a waiting launch only the launches since then matter: buffer 1 is free to be reused
     assert _pdl([L(0, 1), L(2, 3), L(4, 3), L(6, 1)]) == [1, 0, 1, 0]
+
+
+def _chunk_plan(lib, n, H=128, W=128, pipelined=0):
+    sizes = np.zeros(4096, np.int64)
+    k = lib.cnnacc_chunk_plan_host(n, H, W, pipelined, sizes.ctypes.data_as(ctypes.c_void_p), sizes.size)
+    assert k > 0, (n, H, W, pipelined, k)
+    return [int(v) for v in sizes[:k]]
+
+
+def test_host_chunk_plans_cover_every_call_once(lib):
+    """How host-pointer calls are cut into staging chunks (csrc/host_chunks.h): every plan covers the call exactly once with
+    chunks of 1..full images; synchronous calls ramp 1/4, 1/2, 1 ... 1, 1/2, 1/4; streamed calls use one chunk up to 64 MiB."""
+    # the bench's e2e batch, by hand: 64 MiB call -> 16 MiB chunks (1024 images), ramp depth 2
+    assert _chunk_plan(lib, 4096) == [256, 512, 1024, 1024, 512, 512, 256]
+    assert _chunk_plan(lib, 4096, pipelined=1) == [4096]
+    assert _chunk_plan(lib, 16384, pipelined=1) == [4096] * 4
+    assert _chunk_plan(lib, 16384 + 5, pipelined=1) == [4096] * 4 + [5]
+    assert _chunk_plan(lib, 1) == [1] and _chunk_plan(lib, 1, pipelined=1) == [1]
+    assert _chunk_plan(lib, 65) == [65]                                   # < 4 MiB: one chunk
+    rng = np.random.default_rng(0)
+    cases = [(int(n), 128, 128) for n in list(range(1, 40)) + [255, 256, 257, 1023, 1024, 1025, 4095, 4097, 65536, 1 << 20]]
+    cases += [(int(rng.integers(1, 300000)), 128, 128) for _ in range(300)]
+    cases += [(int(rng.integers(1, 3000)), 16 * int(rng.integers(1, 40)), 16 * int(rng.integers(1, 40))) for _ in range(200)]
+    for n, H, W in cases:
+        in_sz = H * W
+        for pipelined in (0, 1):
+            plan = _chunk_plan(lib, n, H, W, pipelined)
+            assert sum(plan) == n and min(plan) >= 1, (n, H, W, pipelined)
+            full = max(plan)
+            cap = (64 << 20) if pipelined else (32 << 20)
+            assert full * in_sz <= max(cap, in_sz) and full * in_sz * 8 <= max(512 << 20, in_sz * 8), (n, H, W, pipelined)
+            if pipelined:
+                assert all(m == full for m in plan[:-1]) and len(plan) == -(-n // full), (n, H, W)
+            else:
+                # ramp: sizes never decrease up to the first full-size chunk; after the last one comes at most one odd-sized
+                # remainder piece and then the halving ramp-down
+                first, last = plan.index(full), len(plan) - 1 - plan[::-1].index(full)
+                down = plan[last + 1:]
+                if len(down) > 1 and down[0] < down[1]:
+                    down = down[1:]
+                assert plan[:first + 1] == sorted(plan[:first + 1]) and down == sorted(down, reverse=True), (n, H, W, plan)
+                assert len(plan) <= n // full + 6, (n, H, W, plan)
+    assert lib.cnnacc_chunk_plan_host(0, 128, 128, 0, None, 0) == fc._lib.ERR_ARG
